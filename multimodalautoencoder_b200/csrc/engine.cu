@@ -1,0 +1,1125 @@
+// libmmae_b200.so -- engine and C ABI (include/mmae_b200.h).
+//
+// One engine = one MMAE graph instance (multimodal_autoencoder.py:344-452): parameters, two Adam
+// states (opt_step :411 and classification_opt_step :443), workspaces and a CUDA stream.
+// Parameter layout in the flat buffer P:  [decoder-only vars | encoder + variance vars | head vars]
+// so that optimizer 0 owns the prefix [0, end_enc) and optimizer 1 the suffix [begin_enc, end).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/mmae_b200.h"
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+using namespace mmae;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Var {
+  std::string name;
+  int64_t rows, cols;   // cols == 0 for vectors (biases); count = rows*max(cols,1)
+  int64_t off;
+  float l2[2];          // L2 coefficient under optimizer 0 / 1
+  int group;            // 0 decoder-only, 1 encoder+variance, 2 head
+  int64_t count() const { return rows * (cols > 0 ? cols : 1); }
+};
+
+// minimal NCCL binding (dlopen; no link-time dependency so single-GPU users never load it)
+struct Id128 { char b[128]; };
+struct Nccl {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+Nccl g_nccl;
+
+bool load_nccl(std::string& err) {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+  if (!g_nccl.lib) { err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    err = "libnccl is missing a required symbol"; g_nccl.lib = nullptr; return false;
+  }
+  return true;
+}
+
+int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
+
+}  // namespace
+
+struct mmae_engine {
+  // ---- configuration (owned copies)
+  mmae_config cfg;
+  std::vector<int32_t> starts, layers, head;
+  std::vector<uint32_t> type_masks, thresholds;
+  int F, M, L, H, E, C;
+  int device = 0, num_sms = 148;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  std::string err;
+  int sticky = 0;
+
+  // ---- parameters
+  std::vector<Var> vars;
+  int64_t nP = 0, enc_begin = 0, enc_end = 0;     // group boundaries in the flat buffer
+  float *P = nullptr, *G = nullptr;               // G has 8 extra floats: the loss sums (allreduced with it)
+  float *M0 = nullptr, *V0 = nullptr, *M1 = nullptr, *V1 = nullptr;
+  int64_t t_opt[2] = {0, 0};
+  AdamSeg* d_segs[2] = {nullptr, nullptr};
+  int nsegs[2] = {0, 0};
+  double* d_scalars = nullptr;                    // MMAE_NUM_SCALARS doubles
+  double* d_sums = nullptr;                       // 8 doubles: recon, kl, head loss, head correct
+
+  // ---- small device tables
+  uint8_t* d_col_mod = nullptr;
+  int32_t* d_starts = nullptr;
+
+  // ---- workspaces (capacity `cap` rows)
+  int64_t cap = 0;
+  uint32_t *zero_bits = nullptr, *mod_bits = nullptr, *miss_bits = nullptr;
+  int64_t noise_rows = 0;
+  float* xin[2] = {nullptr, nullptr};             // host-fed / gathered batches (double buffered)
+  float* yin[2] = {nullptr, nullptr};
+  cudaEvent_t xin_free[2] = {nullptr, nullptr}, xin_ready[2] = {nullptr, nullptr};
+  int xin_turn = 0;
+  float* noisy = nullptr;
+  std::vector<float*> ea, da, ha;                 // saved activations (encoder / decoder / head)
+  float *mu = nullptr, *lv = nullptr, *eps = nullptr, *emb = nullptr, *glv = nullptr;
+  float* out = nullptr;                           // [cap, F]: delta_L in training, decoded_X otherwise
+  float *dA = nullptr, *dB = nullptr;             // delta ping-pong [cap, maxw]
+  float *hlogits = nullptr, *hdelta = nullptr, *hprobs = nullptr;
+  int32_t* hpreds = nullptr;
+  float* partials = nullptr; int64_t partials_cap = 0;
+  float* colsum_ws = nullptr; int64_t colsum_cap = 0;
+  float* splitk_ws = nullptr; int64_t splitk_cap = 0;
+  int64_t* d_idx = nullptr;
+  int maxw = 0;
+
+  // ---- RNG / sharding
+  uint64_t rng_step = 0;
+  uint32_t cur_step = 0;                          // step used by the in-flight forward/backward pair
+  int64_t global_batch = 0, first_row = 0;        // data-parallel shard description (0 = local batch)
+
+  // ---- resident datasets
+  float* ds_X[2] = {nullptr, nullptr}; float* ds_Y[2] = {nullptr, nullptr};
+  int64_t ds_rows[2] = {0, 0}; int ds_ycols[2] = {0, 0};
+
+  // ---- NCCL
+  void* comm = nullptr; int world = 1, rank = 0;
+
+  int64_t launches = 0;
+
+  // ================================================================= helpers
+  int fail(int code, const std::string& m) { err = m; if (code == MMAE_ERR_CUDA) sticky = code; return code; }
+  int cuda_fail(cudaError_t e, const char* what) {
+    return fail(MMAE_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  }
+#define CK(call)                                                           \
+  do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(_e, #call); } while (0)
+#define CKL(what)                                                          \
+  do { ++launches; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return cuda_fail(_e, what); } while (0)
+#define RET(x) do { int _r = (x); if (_r != 0) return _r; } while (0)
+
+  Var* find(const char* name) {
+    for (auto& v : vars) if (v.name == name) return &v;
+    return nullptr;
+  }
+  float* pvar(const std::string& n) { Var* v = find(n.c_str()); return v ? P + v->off : nullptr; }
+  float* gvar(const std::string& n) { Var* v = find(n.c_str()); return v ? G + v->off : nullptr; }
+  int enc_in(int i) const { return i == 0 ? F : layers[i - 1]; }
+  int grid_for(int64_t n, int block) const {
+    int64_t b = (n + block - 1) / block;
+    int64_t cap_b = (int64_t)num_sms * 8;
+    return (int)std::max<int64_t>(1, std::min(b, cap_b));
+  }
+  NoiseView noise_view(bool on) const {
+    NoiseView nv; nv.zero_bits = zero_bits; nv.mod_bits = mod_bits; nv.col_mod = d_col_mod;
+    nv.zw = (F + 31) / 32; nv.mask_with = cfg.mask_with; nv.enabled = on ? 1 : 0; return nv;
+  }
+  Epilogue epi(int mode) const {
+    Epilogue e; memset(&e, 0, sizeof(e));
+    e.mode = mode; e.keep = 1.f; e.seed = cfg.seed; e.step = cur_step; e.row0 = first_row; return e;
+  }
+  void set_dropout(Epilogue& e, float keep, uint32_t slot, int64_t width) const {
+    e.keep = keep;
+    double t = ceil((double)keep * 16777216.0);
+    e.keep_thr = (uint32_t)std::min(t, 16777216.0);
+    e.drop_stream = kStreamDrop + slot; e.drop_width = width;
+  }
+
+  // ================================================================= construction
+  void add_var(const std::string& n, int64_t r, int64_t c, int group, float l2a, float l2b) {
+    Var v; v.name = n; v.rows = r; v.cols = c; v.group = group; v.off = 0; v.l2[0] = l2a; v.l2[1] = l2b;
+    vars.push_back(v);
+  }
+
+  int build(const mmae_config* c) {
+    cfg = *c;
+    F = c->num_feats; M = c->num_modalities; L = c->num_layers; H = c->num_head_layers;
+    if (F <= 0 || L <= 0 || M <= 0 || M > 32) return fail(MMAE_ERR_INVALID, "need F > 0, L > 0, 0 < M <= 32");
+    if (!c->modality_starts || !c->layer_sizes) return fail(MMAE_ERR_INVALID, "null modality_starts / layer_sizes");
+    starts.assign(c->modality_starts, c->modality_starts + M + 1);
+    layers.assign(c->layer_sizes, c->layer_sizes + L);
+    if (starts[0] != 0 || starts[M] != F) return fail(MMAE_ERR_INVALID, "modality_starts must run from 0 to num_feats");
+    for (int m = 0; m < M; ++m) if (starts[m + 1] < starts[m]) return fail(MMAE_ERR_INVALID, "modality_starts not sorted");
+    for (int l : layers) if (l <= 0) return fail(MMAE_ERR_INVALID, "layer size <= 0");
+    if (H > 0) { if (!c->head_sizes) return fail(MMAE_ERR_INVALID, "null head_sizes"); head.assign(c->head_sizes, c->head_sizes + H); }
+    if (c->variational && L < 2) return fail(MMAE_ERR_INVALID, "variational needs >= 2 layers (multimodal_autoencoder.py:299)");
+    if (c->variational && c->tie_weights) return fail(MMAE_ERR_INVALID, "variational forces untied weights (:177)");
+    if (c->num_noise_types > 8 || c->num_modalities_to_drop > 4 || c->num_modalities_to_drop < 0)
+      return fail(MMAE_ERR_INVALID, "at most 8 noise types and 4 dropped modalities");
+    if (c->noise_mode == MMAE_NOISE_INTELLIGENT) {
+      if (c->num_noise_types < 1 || !c->noise_type_masks || (c->num_noise_types > 1 && !c->noise_thresholds))
+        return fail(MMAE_ERR_INVALID, "intelligent noise needs type masks and thresholds");
+      type_masks.assign(c->noise_type_masks, c->noise_type_masks + c->num_noise_types);
+      if (c->num_noise_types > 1) thresholds.assign(c->noise_thresholds, c->noise_thresholds + c->num_noise_types - 1);
+    }
+    E = layers[L - 1]; C = H > 0 ? head[H - 1] : 0;
+    cfg.modality_starts = nullptr; cfg.layer_sizes = nullptr; cfg.head_sizes = nullptr;
+    cfg.noise_type_masks = nullptr; cfg.noise_thresholds = nullptr;
+
+    CK(cudaGetDevice(&device));
+    CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&xin_free[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&xin_ready[i], cudaEventDisableTiming));
+    }
+
+    // ---- variables, in reference naming (:279-334)
+    const float lam = c->weight_penalty, lamc = c->head_weight_penalty;
+    const bool tied = c->tie_weights != 0;
+    char buf[64];
+    for (int i = 0; i < L; ++i) {
+      if (!tied) { snprintf(buf, 64, "decode_weights%d", i); add_var(buf, layers[i], enc_in(i), 0, lam, 0.f); }
+      snprintf(buf, 64, "decode_biases%d", i); add_var(buf, enc_in(i), 0, 0, 0.f, 0.f);
+    }
+    for (int i = 0; i < L; ++i) {
+      snprintf(buf, 64, "weights%d", i); add_var(buf, enc_in(i), layers[i], 1, tied ? 2.f * lam : lam, 0.f);
+      snprintf(buf, 64, "encode_biases%d", i); add_var(buf, layers[i], 0, 1, 0.f, 0.f);
+    }
+    if (c->variational) {
+      add_var("variance_weights", layers[L - 2], E, 1, lam, 0.f);
+      add_var("variance_bias", E, 0, 1, 0.f, 0.f);
+    }
+    for (int i = 0; i < H; ++i) {
+      int din = i == 0 ? E : head[i - 1];
+      snprintf(buf, 64, "classification_weights%d", i); add_var(buf, din, head[i], 2, 0.f, lamc);
+      snprintf(buf, 64, "classification_biases%d", i); add_var(buf, head[i], 0, 2, 0.f, 0.f);
+    }
+    int64_t off = 0; int prev_group = 0;
+    enc_begin = -1;
+    for (auto& v : vars) {
+      if (v.group >= 1 && enc_begin < 0) enc_begin = off;
+      if (v.group == 2 && prev_group < 2) enc_end = off;
+      prev_group = v.group;
+      v.off = off; off += align4(v.count());
+    }
+    nP = off;
+    if (H == 0) enc_end = nP;
+    if (enc_begin < 0) enc_begin = 0;
+
+    CK(cudaMalloc(&P, nP * 4)); CK(cudaMemset(P, 0, nP * 4));
+    CK(cudaMalloc(&G, (nP + 8) * 4)); CK(cudaMemset(G, 0, (nP + 8) * 4));
+    CK(cudaMalloc(&M0, enc_end * 4)); CK(cudaMemset(M0, 0, enc_end * 4));
+    CK(cudaMalloc(&V0, enc_end * 4)); CK(cudaMemset(V0, 0, enc_end * 4));
+    if (H > 0) {
+      int64_t n1 = nP - enc_begin;
+      CK(cudaMalloc(&M1, n1 * 4)); CK(cudaMemset(M1, 0, n1 * 4));
+      CK(cudaMalloc(&V1, n1 * 4)); CK(cudaMemset(V1, 0, n1 * 4));
+    }
+    CK(cudaMalloc(&d_scalars, MMAE_NUM_SCALARS * 8)); CK(cudaMemset(d_scalars, 0, MMAE_NUM_SCALARS * 8));
+    CK(cudaMalloc(&d_sums, 8 * 8)); CK(cudaMemset(d_sums, 0, 64));
+    for (int o = 0; o < 2; ++o) {
+      std::vector<AdamSeg> segs;
+      for (auto& v : vars) { AdamSeg s; s.begin = v.off; s.l2 = v.l2[o]; s.pad = 0.f; segs.push_back(s); }
+      nsegs[o] = (int)segs.size();
+      CK(cudaMalloc(&d_segs[o], segs.size() * sizeof(AdamSeg)));
+      CK(cudaMemcpy(d_segs[o], segs.data(), segs.size() * sizeof(AdamSeg), cudaMemcpyHostToDevice));
+    }
+    std::vector<uint8_t> cm(F);
+    for (int m = 0; m < M; ++m) for (int cidx = starts[m]; cidx < starts[m + 1]; ++cidx) cm[cidx] = (uint8_t)m;
+    CK(cudaMalloc(&d_col_mod, F)); CK(cudaMemcpy(d_col_mod, cm.data(), F, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_starts, (M + 1) * 4)); CK(cudaMemcpy(d_starts, starts.data(), (M + 1) * 4, cudaMemcpyHostToDevice));
+
+    maxw = E;
+    for (int l : layers) maxw = std::max(maxw, l);
+    for (int h : head) maxw = std::max(maxw, h);
+    ea.assign(L, nullptr); da.assign(L, nullptr); ha.assign(std::max(H, 1), nullptr);
+    return ensure_cap(std::max<int64_t>(c->max_batch, 1));
+  }
+
+  template <class T> int realloc_dev(T*& p, int64_t count) {
+    if (p) { CK(cudaFree(p)); p = nullptr; }
+    CK(cudaMalloc(&p, std::max<int64_t>(count, 1) * sizeof(T)));
+    return 0;
+  }
+
+  int ensure_cap(int64_t B) {
+    if (B <= cap) return 0;
+    CK(cudaStreamSynchronize(stream));
+    int64_t nc = std::max<int64_t>(B, cap + cap / 2);
+    const int zw = (F + 31) / 32;
+    RET(realloc_dev(zero_bits, nc * zw)); RET(realloc_dev(mod_bits, nc)); RET(realloc_dev(miss_bits, nc));
+    noise_rows = 0;
+    for (int i = 0; i < 2; ++i) { RET(realloc_dev(xin[i], nc * F)); RET(realloc_dev(yin[i], nc * std::max(C, 1))); }
+    RET(realloc_dev(noisy, nc * F));
+    for (int i = 0; i + 1 < L; ++i) RET(realloc_dev(ea[i], nc * layers[i]));
+    for (int j = 0; j + 1 < L; ++j) RET(realloc_dev(da[j], nc * layers[L - 2 - j]));
+    RET(realloc_dev(mu, nc * E));
+    if (cfg.variational) { RET(realloc_dev(lv, nc * E)); RET(realloc_dev(eps, nc * E)); RET(realloc_dev(emb, nc * E)); RET(realloc_dev(glv, nc * E)); }
+    RET(realloc_dev(out, nc * F));
+    RET(realloc_dev(dA, nc * maxw)); RET(realloc_dev(dB, nc * maxw));
+    if (H > 0) {
+      for (int i = 0; i < H; ++i) RET(realloc_dev(ha[i], nc * head[i]));
+      RET(realloc_dev(hlogits, nc * C)); RET(realloc_dev(hdelta, nc * C));
+      RET(realloc_dev(hprobs, nc * C)); RET(realloc_dev(hpreds, nc * C));
+    }
+    RET(realloc_dev(d_idx, nc));
+    // loss partials: one per CTA of the largest loss-carrying GEMM (SIMT worst case) or reduction grid
+    int64_t pc = std::max<int64_t>(gemm_simt_num_ctas(nc, F), (int64_t)num_sms * 16) + 16;
+    if (pc > partials_cap) { RET(realloc_dev(partials, pc)); partials_cap = pc; }
+    int64_t cs = (int64_t)64 * std::max(F, maxw);
+    if (cs > colsum_cap) { RET(realloc_dev(colsum_ws, cs)); colsum_cap = cs; }
+    cap = nc;
+    return 0;
+  }
+
+  int ensure_splitk(int64_t count) {
+    if (count <= splitk_cap) return 0;
+    CK(cudaStreamSynchronize(stream));
+    RET(realloc_dev(splitk_ws, count)); splitk_cap = count; return 0;
+  }
+
+  void release() {
+    auto fr = [](void* p) { if (p) cudaFree(p); };
+    fr(P); fr(G); fr(M0); fr(V0); fr(M1); fr(V1); fr(d_scalars); fr(d_sums); fr(d_segs[0]); fr(d_segs[1]);
+    fr(d_col_mod); fr(d_starts); fr(zero_bits); fr(mod_bits); fr(miss_bits);
+    for (int i = 0; i < 2; ++i) { fr(xin[i]); fr(yin[i]); fr(ds_X[i]); fr(ds_Y[i]); }
+    fr(noisy);
+    for (auto p : ea) fr(p); for (auto p : da) fr(p); for (auto p : ha) fr(p);
+    fr(mu); fr(lv); fr(eps); fr(emb); fr(glv); fr(out); fr(dA); fr(dB);
+    fr(hlogits); fr(hdelta); fr(hprobs); fr(hpreds); fr(partials); fr(colsum_ws); fr(splitk_ws); fr(d_idx);
+    for (int i = 0; i < 2; ++i) { if (xin_free[i]) cudaEventDestroy(xin_free[i]); if (xin_ready[i]) cudaEventDestroy(xin_ready[i]); }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+  }
+
+  // ================================================================= GEMM dispatch
+  // C = opA(A) opB(B) with epilogue.  n_partials receives the number of loss partials written.
+  int gemm(bool ta, bool tb, int64_t m, int64_t n, int64_t k, const float* A, int64_t lda, const float* B,
+           int64_t ldb, float* Cp, int64_t ldc, const NoiseView& nv, const Epilogue& ep, int64_t* n_partials,
+           bool allow_splitk) {
+    GemmArgs g; g.M = m; g.N = n; g.K = k; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = Cp; g.ldc = ldc;
+    g.noise = nv; g.ep = ep;
+    if (cfg.precision == MMAE_PREC_TF32 && tc_gemm_eligible(ta, tb, g)) {
+      TcPlan pl = tc_plan(g, num_sms, allow_splitk && ep.mode == EPI_PLAIN ? 64 : 1);
+      if (pl.splits > 1) RET(ensure_splitk((int64_t)pl.splits * m * n));
+      cudaError_t e = launch_gemm_tc(ta, tb, g, pl, splitk_ws, stream);
+      ++launches;
+      if (e != cudaSuccess) return cuda_fail(e, "tcgen05 gemm launch");
+      if (pl.splits > 1) {
+        splitk_reduce_kernel<<<grid_for(m * n, 256), 256, 0, stream>>>(splitk_ws, m * n, pl.splits, Cp, n, ldc, ep.beta);
+        CKL("splitk_reduce");
+      }
+      if (n_partials) *n_partials = pl.grid;
+      return 0;
+    }
+    cudaError_t e = launch_gemm_simt(ta, tb, g, stream);
+    ++launches;
+    if (e != cudaSuccess) return cuda_fail(e, "simt gemm launch");
+    if (n_partials) *n_partials = gemm_simt_num_ctas(m, n);
+    return 0;
+  }
+
+  int colsum(const float* D, int64_t rows, int n, int64_t ld, float* outp) {
+    int splits = (int)std::max<int64_t>(1, std::min<int64_t>(64, rows / 256));
+    dim3 grid((n + 31) / 32, splits), block(32, 8);
+    colsum_partial_kernel<<<grid, block, 0, stream>>>(D, rows, n, ld, colsum_ws, splits);
+    CKL("colsum_partial");
+    colsum_final_kernel<<<(n + 127) / 128, 128, 0, stream>>>(colsum_ws, n, splits, outp);
+    CKL("colsum_final");
+    return 0;
+  }
+
+  int reduce_partials(int64_t n, int slot, bool accumulate = false) {
+    reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, n, d_sums + slot, accumulate ? 1 : 0);
+    CKL("reduce_partials");
+    return 0;
+  }
+
+  // ================================================================= forward (:366-378, :428)
+  struct FwdOpts {
+    const float* X; const float* target; const float* labels;
+    int64_t B; bool noise; float keep; bool train_recon;   // train_recon: last layer emits delta_L
+    bool decoder; bool headp; float* recon_out;
+  };
+
+  int begin_step(int64_t B, bool noise) {
+    if (sticky) return fail(MMAE_ERR_CUDA, "engine is in a sticky CUDA error state: " + err);
+    if (B <= 0) return fail(MMAE_ERR_INVALID, "batch must be > 0");
+    RET(ensure_cap(B));
+    if (noise && noise_rows < B) return fail(MMAE_ERR_STATE, "noise descriptor covers fewer rows than the batch; call mmae_set_noise / mmae_gen_noise first");
+    cur_step = (uint32_t)rng_step;
+    return 0;
+  }
+
+  int forward(const FwdOpts& o) {
+    const int64_t B = o.B;
+    const int act = cfg.activation;
+    const float* a = o.X;
+    NoiseView nv = noise_view(o.noise);
+    if (o.noise && cfg.precision == MMAE_PREC_TF32 && B >= 128 && (F & 3) == 0) {
+      // the tcgen05 family reads its operands through TMA: materialise noisy_X once (first GEMM + its wgrad)
+      noise_apply_kernel<<<grid_for(B * F, 256), 256, 0, stream>>>(o.X, noisy, B, F, nv);
+      CKL("noise_apply");
+      a = noisy; nv.enabled = 0;
+    }
+    x_eff = a; x_noise = nv;
+    int64_t lda = F;
+    for (int i = 0; i < L; ++i) {
+      const bool last = i == L - 1;
+      const int din = enc_in(i), dout = layers[i];
+      char wn[32], bn[32]; snprintf(wn, 32, "weights%d", i); snprintf(bn, 32, "encode_biases%d", i);
+      NoiseView lnv = i == 0 ? nv : noise_view(false);
+      if (cfg.variational && last) {
+        Epilogue e = epi(EPI_BIAS_ACT); e.bias = pvar("variance_bias"); e.act = MMAE_ACT_LINEAR;
+        RET(gemm(false, false, B, E, din, a, lda, pvar("variance_weights"), E, lv, E, lnv, e, nullptr, false));
+      }
+      Epilogue e = epi(EPI_BIAS_ACT); e.bias = pvar(bn);
+      float* dst;
+      if (!last) { e.act = act; if (o.keep < 1.f) set_dropout(e, o.keep, (uint32_t)i, dout); dst = ea[i]; }
+      else { e.act = MMAE_ACT_LINEAR; dst = mu; }
+      RET(gemm(false, false, B, dout, din, a, lda, pvar(wn), dout, dst, dout, lnv, e, nullptr, false));
+      a = dst; lda = dout;
+    }
+    cur_emb = mu;
+    if (cfg.variational) {
+      VaeArgs va; va.mu = mu; va.lv = lv; va.eps = eps; va.emb = emb; va.kl_partials = partials;
+      va.batch = B; va.row0 = first_row; va.E = E; va.step = cur_step; va.seed = cfg.seed; va.gen_eps = eps_injected ? 0 : 1;
+      int g = grid_for(B * E, 256);
+      vae_sample_kernel<<<g, 256, 0, stream>>>(va);
+      CKL("vae_sample");
+      RET(reduce_partials(g, 1));
+      cur_emb = emb;
+    }
+    if (o.decoder) {
+      const float* u = cur_emb; int64_t ldu = E;
+      for (int j = 0; j < L; ++j) {
+        const int i = L - 1 - j;
+        const int din = layers[i], dout = enc_in(i);
+        const bool last = j == L - 1;
+        char wn[32], bn[32];
+        snprintf(bn, 32, "decode_biases%d", i);
+        const float* W; bool tb; int64_t ldw;
+        if (cfg.tie_weights) { snprintf(wn, 32, "weights%d", i); W = pvar(wn); tb = true; ldw = din; }   // W_i^T (:284)
+        else { snprintf(wn, 32, "decode_weights%d", i); W = pvar(wn); tb = false; ldw = dout; }
+        Epilogue e; float* dst;
+        int64_t np = 0;
+        if (!last) {
+          e = epi(EPI_BIAS_ACT); e.bias = pvar(bn); e.act = act;
+          if (o.keep < 1.f) set_dropout(e, o.keep, 32u + (uint32_t)j, dout);
+          dst = da[j];
+          RET(gemm(false, tb, B, dout, din, u, ldu, W, ldw, dst, dout, noise_view(false), e, nullptr, false));
+        } else {
+          e = epi(o.train_recon ? EPI_LOSS_TRAIN : EPI_LOSS_PRED); e.bias = pvar(bn); e.loss = cfg.loss_func;
+          e.target = o.target; e.ldt = F; e.loss_partials = o.target ? partials : nullptr;
+          dst = o.recon_out ? o.recon_out : out;
+          RET(gemm(false, tb, B, dout, din, u, ldu, W, ldw, dst, dout, noise_view(false), e, &np, false));
+          if (o.target) RET(reduce_partials(np, 0));
+        }
+        u = dst; ldu = dout;
+      }
+    }
+    if (o.headp) {
+      const float* h = cur_emb; int64_t ldh = E;
+      for (int i = 0; i < H; ++i) {
+        const int din = i == 0 ? E : head[i - 1], dout = head[i];
+        char wn[40], bn[40]; snprintf(wn, 40, "classification_weights%d", i); snprintf(bn, 40, "classification_biases%d", i);
+        Epilogue e = epi(EPI_BIAS_ACT); e.bias = pvar(bn);
+        const bool activated = i < L - 1;                   // reference quirk: bound is the AE depth (:533)
+        if (activated) { e.act = cfg.head_activation; if (o.keep < 1.f) set_dropout(e, o.keep, 64u + (uint32_t)i, dout); }
+        else e.act = MMAE_ACT_LINEAR;
+        float* dst = (i == H - 1) ? hlogits : ha[i];
+        RET(gemm(false, false, B, dout, din, h, ldh, pvar(wn), dout, dst, dout, noise_view(false), e, nullptr, false));
+        h = dst; ldh = dout;
+      }
+    }
+    return 0;
+  }
+  const float* x_eff = nullptr; NoiseView x_noise; const float* cur_emb = nullptr;
+  bool eps_injected = false;
+
+  int64_t gbatch(int64_t B) const { return global_batch > 0 ? global_batch : B; }
+
+  int head_loss(const float* labels, int64_t B, bool want_delta, float* probs, int32_t* preds) {
+    HeadLossArgs a; a.logits = hlogits; a.labels = labels; a.delta = want_delta ? hdelta : nullptr;
+    a.probs = probs; a.preds = preds; a.partials = partials; a.batch = B; a.C = C; a.loss = cfg.head_loss;
+    const double cnt = cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? (double)gbatch(B) * C : (double)gbatch(B);
+    a.inv_count = (float)(1.0 / cnt);
+    int g = (int)std::max<int64_t>(1, std::min<int64_t>((B + 127) / 128, num_sms * 4));
+    head_loss_kernel<<<g, 128, 0, stream>>>(a);
+    CKL("head_loss");
+    if (labels) {
+      reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, g, d_sums + 2, 0); CKL("reduce_partials");
+      reduce_partials_kernel<<<1, 256, 0, stream>>>(partials + g, g, d_sums + 3, 0); CKL("reduce_partials");
+    }
+    return 0;
+  }
+
+  // ================================================================= backward
+  // Encoder part shared by both optimizers.  d = dL/dmu [B,E] in `d`; g_lv in glv when variational.
+  int backward_encoder(int64_t B, float* d, float keep) {
+    float* other = (d == dA) ? dB : dA;
+    for (int i = L - 1; i >= 0; --i) {
+      const int din = enc_in(i), dout = layers[i];
+      char wn[32], bn[32]; snprintf(wn, 32, "weights%d", i); snprintf(bn, 32, "encode_biases%d", i);
+      const float* a_in = i == 0 ? x_eff : ea[i - 1];
+      NoiseView nv = i == 0 ? x_noise : noise_view(false);
+      RET(colsum(d, B, dout, dout, gvar(bn)));
+      Epilogue ew = epi(EPI_PLAIN); ew.beta = (cfg.tie_weights && !cls_pass) ? 1.f : 0.f;   // tied: decoder part already there
+      RET(gemm(true, false, din, dout, B, a_in, din, d, dout, gvar(wn), dout, nv, ew, nullptr, true));
+      if (i == 0) break;
+      const bool var_here = cfg.variational && i == L - 1;
+      Epilogue ed = epi(var_here ? EPI_PLAIN : EPI_DGRAD);
+      if (!var_here) { ed.saved = ea[i - 1]; ed.lds = din; ed.act = cfg.activation; if (keep < 1.f) set_dropout(ed, keep, (uint32_t)(i - 1), din); }
+      RET(gemm(false, true, B, din, dout, d, dout, pvar(wn), dout, other, din, noise_view(false), ed, nullptr, false));
+      if (var_here) {
+        RET(colsum(glv, B, E, E, gvar("variance_bias")));
+        Epilogue ev = epi(EPI_PLAIN);
+        RET(gemm(true, false, din, E, B, a_in, din, glv, E, gvar("variance_weights"), E, noise_view(false), ev, nullptr, true));
+        Epilogue e2 = epi(EPI_DGRAD); e2.beta = 1.f; e2.saved = ea[i - 1]; e2.lds = din; e2.act = cfg.activation;
+        if (keep < 1.f) set_dropout(e2, keep, (uint32_t)(i - 1), din);
+        RET(gemm(false, true, B, din, E, glv, E, pvar("variance_weights"), E, other, din, noise_view(false), e2, nullptr, false));
+      }
+      std::swap(d, other);
+    }
+    return 0;
+  }
+  bool cls_pass = false;
+
+  int backward_recon(int64_t B, float keep) {
+    cls_pass = false;
+    float* d = out; int64_t ldd = F;       // delta_L from the EPI_LOSS_TRAIN epilogue
+    float* nxt = dA;
+    for (int j = L - 1; j >= 0; --j) {
+      const int i = L - 1 - j;
+      const int din = layers[i], dout = enc_in(i);     // decoder layer maps din -> dout
+      char wn[32], bn[32]; snprintf(bn, 32, "decode_biases%d", i);
+      const float* u_in = j == 0 ? cur_emb : da[j - 1];
+      RET(colsum(d, B, dout, ldd, gvar(bn)));
+      Epilogue ew = epi(EPI_PLAIN);
+      if (cfg.tie_weights) {   // (dD)^T = delta^T . u accumulates into the tied encoder variable
+        snprintf(wn, 32, "weights%d", i);
+        RET(gemm(true, false, dout, din, B, d, ldd, u_in, din, gvar(wn), din, noise_view(false), ew, nullptr, true));
+      } else {
+        snprintf(wn, 32, "decode_weights%d", i);
+        RET(gemm(true, false, din, dout, B, u_in, din, d, ldd, gvar(wn), dout, noise_view(false), ew, nullptr, true));
+      }
+      Epilogue ed = epi(j > 0 ? EPI_DGRAD : EPI_PLAIN);
+      if (j > 0) { ed.saved = da[j - 1]; ed.lds = din; ed.act = cfg.activation; if (keep < 1.f) set_dropout(ed, keep, 32u + (uint32_t)(j - 1), din); }
+      // g_u = delta . D^T : untied D stored [din, dout] = [N, K] -> transposed B operand; tied D^T = W_i stored [dout, din] = [K, N]
+      RET(gemm(false, !cfg.tie_weights, B, din, dout, d, ldd, pvar(wn), cfg.tie_weights ? din : dout, nxt, din,
+               noise_view(false), ed, nullptr, false));
+      d = nxt; ldd = din; nxt = (nxt == dA) ? dB : dA;
+    }
+    if (cfg.variational) {
+      vae_grad_kernel<<<grid_for(B * E, 256), 256, 0, stream>>>(d, glv, emb, lv, eps, B * E, (float)(1.0 / (double)gbatch(B)));
+      CKL("vae_grad");
+    }
+    return backward_encoder(B, d, keep);
+  }
+
+  int backward_cls(int64_t B, float keep) {
+    cls_pass = true;
+    float* d = hdelta; int64_t ldd = C;
+    float* nxt = dA;
+    if (H - 1 < L - 1) {     // quirk (:533): the logits themselves went through act + dropout
+      // d <- d * act'(logits) * dropmask/keep, done by a 1-column-block "GEMM-free" pass: reuse the dgrad epilogue
+      Epilogue ed = epi(EPI_DGRAD); ed.saved = hlogits; ed.lds = C; ed.act = cfg.head_activation;
+      if (keep < 1.f) set_dropout(ed, keep, 64u + (uint32_t)(H - 1), C);
+      elementwise_epilogue_kernel<<<grid_for(B * C, 256), 256, 0, stream>>>(d, B, C, ed);
+      CKL("head_logit_act_grad");
+    }
+    for (int i = H - 1; i >= 0; --i) {
+      const int din = i == 0 ? E : head[i - 1], dout = head[i];
+      char wn[40], bn[40]; snprintf(wn, 40, "classification_weights%d", i); snprintf(bn, 40, "classification_biases%d", i);
+      const float* u_in = i == 0 ? cur_emb : ha[i - 1];
+      RET(colsum(d, B, dout, ldd, gvar(bn)));
+      Epilogue ew = epi(EPI_PLAIN);
+      RET(gemm(true, false, din, dout, B, u_in, din, d, ldd, gvar(wn), dout, noise_view(false), ew, nullptr, true));
+      const bool act_prev = i > 0 && (i - 1) < L - 1;
+      Epilogue ed = epi(act_prev ? EPI_DGRAD : EPI_PLAIN);
+      if (act_prev) { ed.saved = ha[i - 1]; ed.lds = din; ed.act = cfg.head_activation; if (keep < 1.f) set_dropout(ed, keep, 64u + (uint32_t)(i - 1), din); }
+      RET(gemm(false, true, B, din, dout, d, ldd, pvar(wn), dout, nxt, din, noise_view(false), ed, nullptr, false));
+      d = nxt; ldd = din; nxt = (nxt == dA) ? dB : dA;
+    }
+    if (cfg.variational) {
+      vae_grad_kernel<<<grid_for(B * E, 256), 256, 0, stream>>>(d, glv, emb, lv, eps, B * E, 0.f);
+      CKL("vae_grad");
+    }
+    return backward_encoder(B, d, keep);
+  }
+
+  // ================================================================= sums -> G tail -> allreduce -> scalars
+  int pack_sums() {
+    pack_sums_kernel<<<1, 32, 0, stream>>>(d_sums, G + nP, 1); CKL("pack_sums"); return 0;
+  }
+  int unpack_sums() {
+    pack_sums_kernel<<<1, 32, 0, stream>>>(d_sums, G + nP, 0); CKL("unpack_sums"); return 0;
+  }
+  int allreduce_grads() {
+    if (!comm || world <= 1) return 0;
+    RET(pack_sums());
+    int r = g_nccl.AllReduce(G, G, (size_t)(nP + 8), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, stream);
+    if (r != 0) return fail(MMAE_ERR_COMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    RET(unpack_sums());
+    return 0;
+  }
+  int finalize_scalars(int64_t B, bool recon, bool headl) {
+    FinalizeArgs a; a.sums = d_sums; a.scalars = d_scalars; a.loss = cfg.loss_func; a.variational = cfg.variational;
+    a.n_elems = (double)gbatch(B) * F; a.batch = (double)gbatch(B);
+    a.head_count = cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? (double)gbatch(B) * std::max(C, 1) : (double)gbatch(B);
+    a.do_recon = recon ? 1 : 0; a.do_head = headl ? 1 : 0;
+    finalize_scalars_kernel<<<1, 1, 0, stream>>>(a); CKL("finalize_scalars"); return 0;
+  }
+
+  int apply_update(int opt, int64_t B) {
+    if (opt == 1 && H == 0) return fail(MMAE_ERR_STATE, "no classification head");
+    t_opt[opt] += 1;
+    const double t = (double)t_opt[opt];
+    const double lr = opt == 0 ? cfg.learning_rate : cfg.head_learning_rate;
+    AdamArgs a; a.P = P; a.G = G;
+    a.M = opt == 0 ? M0 : M1; a.V = opt == 0 ? V0 : V1;
+    a.begin = opt == 0 ? 0 : enc_begin; a.end = opt == 0 ? enc_end : nP;
+    a.segs = d_segs[opt]; a.nsegs = nsegs[opt]; a.sums = d_sums;
+    a.scale_mode = (opt == 0 && cfg.loss_func == MMAE_LOSS_RMSE) ? 1 : 0;
+    a.n_elems = (double)gbatch(B) * F;
+    a.alpha = (float)(lr * sqrt(1.0 - pow((double)cfg.beta2, t)) / (1.0 - pow((double)cfg.beta1, t)));
+    a.b1 = cfg.beta1; a.b2 = cfg.beta2; a.eps = cfg.adam_eps; a.scalars_out = d_scalars;
+    adam_kernel<<<grid_for(a.end - a.begin, 256), 256, 0, stream>>>(a);
+    CKL("adam");
+    return 0;
+  }
+  int64_t last_B = 0;
+  int64_t pending_global = 0;
+};
+
+
+// =====================================================================================================
+//                                             C ABI
+// =====================================================================================================
+namespace {
+struct DeviceGuard {   // engines are bound to the device that was current at create time
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ENTER(e)                                                        \
+  if (!(e)) return MMAE_ERR_INVALID;                                    \
+  DeviceGuard _guard((e)->device)
+
+int launch_noise_gen(mmae_engine* e, int64_t batch, int64_t first_row) {
+  NoiseGenArgs a; memset(&a, 0, sizeof(a));
+  a.zero_bits = e->zero_bits; a.mod_bits = e->mod_bits; a.batch = batch; a.row0 = first_row;
+  a.num_feats = e->F; a.zw = (e->F + 31) / 32; a.n_zero = e->cfg.n_zero; a.num_mod = e->M;
+  a.mode = e->cfg.noise_mode; a.num_types = (int)e->type_masks.size(); a.num_drop = e->cfg.num_modalities_to_drop;
+  for (size_t i = 0; i < e->thresholds.size(); ++i) a.thresholds[i] = e->thresholds[i];
+  for (size_t i = 0; i < e->type_masks.size(); ++i) a.type_masks[i] = e->type_masks[i];
+  a.step = (uint32_t)e->rng_step; a.seed = e->cfg.seed;
+  const int wpb = 8;
+  noise_gen_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(a);
+  ++e->launches;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return e->cuda_fail(err, "noise_gen");
+  e->noise_rows = batch;
+  return 0;
+}
+
+int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float keep) {
+  int r = e->begin_step(B, use_noise != 0); if (r) return r;
+  mmae_engine::FwdOpts o; o.X = X; o.target = X; o.labels = nullptr; o.B = B; o.noise = use_noise != 0; o.keep = keep;
+  o.train_recon = true; o.decoder = true; o.headp = false; o.recon_out = nullptr;
+  r = e->forward(o); if (r) return r;
+  r = e->backward_recon(B, keep); if (r) return r;
+  e->last_B = B;
+  e->rng_step += 1;
+  return 0;
+}
+
+int do_cls(mmae_engine* e, const float* X, const float* Y, int64_t B, int use_noise, float keep) {
+  if (e->H == 0) return e->fail(MMAE_ERR_STATE, "engine was created without a classification head");
+  int r = e->begin_step(B, use_noise != 0); if (r) return r;
+  mmae_engine::FwdOpts o; o.X = X; o.target = nullptr; o.labels = Y; o.B = B; o.noise = use_noise != 0; o.keep = keep;
+  o.train_recon = false; o.decoder = false; o.headp = true; o.recon_out = nullptr;
+  r = e->forward(o); if (r) return r;
+  r = e->head_loss(Y, B, true, nullptr, nullptr); if (r) return r;
+  r = e->backward_cls(B, keep); if (r) return r;
+  e->last_B = B;
+  e->rng_step += 1;
+  return 0;
+}
+
+// stage a host batch into the double-buffered device input; returns the device pointers
+int stage_host(mmae_engine* e, const float* X_host, const float* Y_host, int64_t B, int ycols, float** Xd, float** Yd) {
+  int r = e->ensure_cap(B); if (r) return r;
+  const int t = e->xin_turn; e->xin_turn ^= 1;
+  cudaError_t ce;
+  // the copy may start once the compute that last read this buffer has finished
+  if ((ce = cudaStreamWaitEvent(e->copy_stream, e->xin_free[t], 0)) != cudaSuccess) return e->cuda_fail(ce, "wait xin_free");
+  if ((ce = cudaMemcpyAsync(e->xin[t], X_host, (size_t)B * e->F * 4, cudaMemcpyHostToDevice, e->copy_stream)) != cudaSuccess)
+    return e->cuda_fail(ce, "H2D X");
+  if (Y_host && ycols > 0)
+    if ((ce = cudaMemcpyAsync(e->yin[t], Y_host, (size_t)B * ycols * 4, cudaMemcpyHostToDevice, e->copy_stream)) != cudaSuccess)
+      return e->cuda_fail(ce, "H2D Y");
+  if ((ce = cudaEventRecord(e->xin_ready[t], e->copy_stream)) != cudaSuccess) return e->cuda_fail(ce, "record xin_ready");
+  if ((ce = cudaStreamWaitEvent(e->stream, e->xin_ready[t], 0)) != cudaSuccess) return e->cuda_fail(ce, "wait xin_ready");
+  *Xd = e->xin[t]; if (Yd) *Yd = e->yin[t];
+  return t;
+}
+int release_stage(mmae_engine* e, int t) {
+  cudaError_t ce = cudaEventRecord(e->xin_free[t], e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "record xin_free");
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int mmae_create(const mmae_config* cfg, mmae_engine** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return MMAE_ERR_INVALID; }
+  mmae_engine* e = new mmae_engine();
+  int r = e->build(cfg);
+  if (r != 0) { g_create_error = e->err; e->release(); delete e; *out = nullptr; return r; }
+  *out = e;
+  return MMAE_OK;
+}
+
+void mmae_destroy(mmae_engine* e) {
+  if (!e) return;
+  DeviceGuard g(e->device);
+  cudaStreamSynchronize(e->stream);
+  cudaStreamSynchronize(e->copy_stream);
+  e->release();
+  delete e;
+}
+
+const char* mmae_last_error(const mmae_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int mmae_set_stream(mmae_engine* e, void* s) { ENTER(e); e->stream = (cudaStream_t)s; return 0; }
+
+int mmae_synchronize(mmae_engine* e) {
+  ENTER(e);
+  cudaError_t ce = cudaStreamSynchronize(e->copy_stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "synchronize");
+  return 0;
+}
+
+int mmae_num_variables(const mmae_engine* e) { return e ? (int)e->vars.size() : 0; }
+
+int mmae_variable_info(const mmae_engine* e, int index, char* name_out, int name_cap, int64_t* rows, int64_t* cols) {
+  if (!e || index < 0 || index >= (int)e->vars.size()) return MMAE_ERR_INVALID;
+  const Var& v = e->vars[index];
+  if (name_out && name_cap > 0) { strncpy(name_out, v.name.c_str(), name_cap - 1); name_out[name_cap - 1] = 0; }
+  if (rows) *rows = v.rows;
+  if (cols) *cols = v.cols;
+  return 0;
+}
+
+static int var_copy(mmae_engine* e, const char* name, float* base, int64_t base_off, float* host, int64_t count, bool to_dev) {
+  Var* v = e->find(name);
+  if (!v) return e->fail(MMAE_ERR_NOTFOUND, std::string("unknown variable ") + name);
+  if (count != v->count()) return e->fail(MMAE_ERR_INVALID, std::string("size mismatch for ") + name);
+  cudaError_t ce = cudaStreamSynchronize(e->stream);
+  if (ce == cudaSuccess)
+    ce = to_dev ? cudaMemcpy(base + v->off - base_off, host, count * 4, cudaMemcpyHostToDevice)
+                : cudaMemcpy(host, base + v->off - base_off, count * 4, cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "variable copy");
+  return 0;
+}
+
+int mmae_set_variable(mmae_engine* e, const char* name, const float* host, int64_t count) {
+  ENTER(e); return var_copy(e, name, e->P, 0, const_cast<float*>(host), count, true);
+}
+int mmae_get_variable(mmae_engine* e, const char* name, float* host, int64_t count) {
+  ENTER(e); return var_copy(e, name, e->P, 0, host, count, false);
+}
+int mmae_get_gradient(mmae_engine* e, const char* name, float* host, int64_t count) {
+  ENTER(e); return var_copy(e, name, e->G, 0, host, count, false);
+}
+
+static int opt_check(mmae_engine* e, int opt, const char* name) {
+  Var* v = e->find(name);
+  if (!v) return e->fail(MMAE_ERR_NOTFOUND, std::string("unknown variable ") + name);
+  if (opt == 0 && v->group == 2) return e->fail(MMAE_ERR_INVALID, "optimizer 0 does not own head variables");
+  if (opt == 1 && (v->group == 0 || e->H == 0)) return e->fail(MMAE_ERR_INVALID, "optimizer 1 does not own decoder variables");
+  if (opt != 0 && opt != 1) return e->fail(MMAE_ERR_INVALID, "optimizer must be 0 or 1");
+  return 0;
+}
+int mmae_get_opt_state(mmae_engine* e, int opt, const char* name, float* m_host, float* v_host, int64_t count, int64_t* t) {
+  ENTER(e);
+  int r = opt_check(e, opt, name); if (r) return r;
+  const int64_t base = opt == 0 ? 0 : e->enc_begin;
+  if (m_host) { r = var_copy(e, name, opt == 0 ? e->M0 : e->M1, base, m_host, count, false); if (r) return r; }
+  if (v_host) { r = var_copy(e, name, opt == 0 ? e->V0 : e->V1, base, v_host, count, false); if (r) return r; }
+  if (t) *t = e->t_opt[opt];
+  return 0;
+}
+int mmae_set_opt_state(mmae_engine* e, int opt, const char* name, const float* m_host, const float* v_host, int64_t count, int64_t t) {
+  ENTER(e);
+  int r = opt_check(e, opt, name); if (r) return r;
+  const int64_t base = opt == 0 ? 0 : e->enc_begin;
+  if (m_host) { r = var_copy(e, name, opt == 0 ? e->M0 : e->M1, base, const_cast<float*>(m_host), count, true); if (r) return r; }
+  if (v_host) { r = var_copy(e, name, opt == 0 ? e->V0 : e->V1, base, const_cast<float*>(v_host), count, true); if (r) return r; }
+  if (t >= 0) e->t_opt[opt] = t;
+  return 0;
+}
+
+int mmae_set_rng_step(mmae_engine* e, uint64_t step) { ENTER(e); e->rng_step = step; return 0; }
+
+int mmae_set_noise(mmae_engine* e, const uint32_t* zero_bits_host, const uint32_t* mod_bits_host, int64_t batch) {
+  ENTER(e);
+  if (!zero_bits_host || !mod_bits_host || batch <= 0) return e->fail(MMAE_ERR_INVALID, "null descriptor");
+  int r = e->ensure_cap(batch); if (r) return r;
+  const int zw = (e->F + 31) / 32;
+  cudaError_t ce = cudaMemcpyAsync(e->zero_bits, zero_bits_host, (size_t)batch * zw * 4, cudaMemcpyHostToDevice, e->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->mod_bits, mod_bits_host, (size_t)batch * 4, cudaMemcpyHostToDevice, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);     // host buffers may be pageable / reused
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "set_noise");
+  e->noise_rows = batch;
+  return 0;
+}
+
+int mmae_gen_noise(mmae_engine* e, int64_t batch, int64_t first_row) {
+  ENTER(e);
+  if (batch <= 0) return e->fail(MMAE_ERR_INVALID, "batch must be > 0");
+  int r = e->ensure_cap(batch); if (r) return r;
+  return launch_noise_gen(e, batch, first_row);
+}
+
+int mmae_get_noise(mmae_engine* e, uint32_t* zero_bits_host, uint32_t* mod_bits_host, int64_t batch) {
+  ENTER(e);
+  if (batch > e->noise_rows) return e->fail(MMAE_ERR_STATE, "descriptor has fewer rows");
+  const int zw = (e->F + 31) / 32;
+  cudaError_t ce = cudaStreamSynchronize(e->stream);
+  if (ce == cudaSuccess && zero_bits_host) ce = cudaMemcpy(zero_bits_host, e->zero_bits, (size_t)batch * zw * 4, cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess && mod_bits_host) ce = cudaMemcpy(mod_bits_host, e->mod_bits, (size_t)batch * 4, cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "get_noise");
+  return 0;
+}
+
+int mmae_apply_noise(mmae_engine* e, const float* X_dev, int64_t batch, float* out_dev) {
+  ENTER(e);
+  if (batch > e->noise_rows) return e->fail(MMAE_ERR_STATE, "descriptor has fewer rows than the batch");
+  noise_apply_kernel<<<e->grid_for(batch * e->F, 256), 256, 0, e->stream>>>(X_dev, out_dev, batch, e->F, e->noise_view(true));
+  ++e->launches;
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "noise_apply");
+  return 0;
+}
+
+int mmae_forward(mmae_engine* e, const float* X_dev, const float* target_dev, const float* labels_dev, int64_t batch,
+                 int use_noise, float keep, uint32_t want, const mmae_outputs* out) {
+  ENTER(e);
+  if (!X_dev) return e->fail(MMAE_ERR_INVALID, "null X");
+  const bool need_head = (want & (MMAE_WANT_HEAD | MMAE_WANT_HEAD_LOSS)) != 0;
+  if (need_head && e->H == 0) return e->fail(MMAE_ERR_STATE, "engine was created without a classification head");
+  if ((want & MMAE_WANT_HEAD_LOSS) && !labels_dev) return e->fail(MMAE_ERR_INVALID, "head loss needs labels");
+  const bool need_dec = (want & (MMAE_WANT_RECON | MMAE_WANT_LOSS | MMAE_WANT_FILLED)) != 0;
+  int r = e->begin_step(batch, use_noise != 0); if (r) return r;
+  mmae_engine::FwdOpts o; o.X = X_dev; o.B = batch; o.noise = use_noise != 0; o.keep = keep;
+  o.target = (want & MMAE_WANT_LOSS) ? (target_dev ? target_dev : X_dev) : nullptr;
+  o.labels = labels_dev; o.train_recon = false; o.decoder = need_dec; o.headp = need_head;
+  o.recon_out = (out && (want & MMAE_WANT_RECON)) ? out->recon : nullptr;
+  r = e->forward(o); if (r) return r;
+  cudaError_t ce = cudaSuccess;
+  if ((want & MMAE_WANT_EMBEDDING) && out && out->embedding)
+    ce = cudaMemcpyAsync(out->embedding, e->cur_emb, (size_t)batch * e->E * 4, cudaMemcpyDeviceToDevice, e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "embedding copy");
+  if ((want & MMAE_WANT_FILLED) && out && out->filled) {
+    const float* rec = o.recon_out ? o.recon_out : e->out;
+    const int wpb = 8;
+    missing_bits_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(X_dev, batch, e->F, e->d_starts, e->M, e->miss_bits);
+    ++e->launches;
+    fill_select_kernel<<<e->grid_for(batch * e->F, 256), 256, 0, e->stream>>>(X_dev, rec, e->miss_bits, e->d_col_mod, out->filled, batch, e->F);
+    ++e->launches;
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "fill-in");
+  }
+  if (need_head) {
+    r = e->head_loss((want & MMAE_WANT_HEAD_LOSS) ? labels_dev : nullptr, batch, false,
+                     out ? out->probs : nullptr, out ? out->preds : nullptr);
+    if (r) return r;
+    if (out && out->logits) {
+      ce = cudaMemcpyAsync(out->logits, e->hlogits, (size_t)batch * e->C * 4, cudaMemcpyDeviceToDevice, e->stream);
+      if (ce != cudaSuccess) return e->cuda_fail(ce, "logits copy");
+    }
+  }
+  r = e->finalize_scalars(batch, (want & MMAE_WANT_LOSS) != 0, (want & MMAE_WANT_HEAD_LOSS) != 0); if (r) return r;
+  if (use_noise || keep < 1.f || e->cfg.variational) e->rng_step += 1;
+  e->last_B = batch;
+  return 0;
+}
+
+int mmae_backward(mmae_engine* e, const float* X_dev, int64_t batch, int64_t global_batch, int use_noise, float keep) {
+  ENTER(e);
+  const int64_t saved = e->global_batch;
+  if (global_batch > 0) e->global_batch = global_batch;
+  int r = do_train(e, X_dev, batch, use_noise, keep);
+  if (r == 0) r = e->pack_sums();
+  e->global_batch = saved;
+  if (global_batch > 0) e->pending_global = global_batch; else e->pending_global = 0;
+  return r;
+}
+
+int mmae_grad_buffer(mmae_engine* e, float** dev_ptr, int64_t* count) {
+  ENTER(e);
+  if (dev_ptr) *dev_ptr = e->G;
+  if (count) *count = e->nP + 8;
+  return 0;
+}
+
+int mmae_apply_update(mmae_engine* e, int optimizer) {
+  ENTER(e);
+  const int64_t saved = e->global_batch;
+  if (e->pending_global > 0) e->global_batch = e->pending_global;
+  int r = e->unpack_sums();
+  if (r == 0) r = e->finalize_scalars(e->last_B, optimizer == 0, optimizer == 1);
+  if (r == 0) r = e->apply_update(optimizer, e->last_B);
+  e->global_batch = saved;
+  return r;
+}
+
+int mmae_train_step(mmae_engine* e, const float* X_dev, int64_t batch, int use_noise, float keep) {
+  ENTER(e);
+  int r = do_train(e, X_dev, batch, use_noise, keep); if (r) return r;
+  r = e->allreduce_grads(); if (r) return r;
+  r = e->finalize_scalars(batch, true, false); if (r) return r;
+  return e->apply_update(0, batch);
+}
+
+int mmae_cls_train_step(mmae_engine* e, const float* X_dev, const float* labels_dev, int64_t batch, int use_noise, float keep) {
+  ENTER(e);
+  int r = do_cls(e, X_dev, labels_dev, batch, use_noise, keep); if (r) return r;
+  r = e->allreduce_grads(); if (r) return r;
+  r = e->finalize_scalars(batch, false, true); if (r) return r;
+  return e->apply_update(1, batch);
+}
+
+int mmae_train_step_host(mmae_engine* e, const float* X_host, int64_t batch, int gen_noise, float keep) {
+  ENTER(e);
+  float* Xd = nullptr;
+  int t = stage_host(e, X_host, nullptr, batch, 0, &Xd, nullptr); if (t < 0) return t;
+  if (gen_noise) { int r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }
+  int r = do_train(e, Xd, batch, gen_noise || e->noise_rows >= batch ? (gen_noise ? 1 : 0) : 0, keep); if (r) return r;
+  r = release_stage(e, t); if (r) return r;
+  r = e->allreduce_grads(); if (r) return r;
+  r = e->finalize_scalars(batch, true, false); if (r) return r;
+  return e->apply_update(0, batch);
+}
+
+int mmae_cls_train_step_host(mmae_engine* e, const float* X_host, const float* labels_host, int64_t batch, int gen_noise, float keep) {
+  ENTER(e);
+  if (e->H == 0) return e->fail(MMAE_ERR_STATE, "engine was created without a classification head");
+  float *Xd = nullptr, *Yd = nullptr;
+  const int ycols = e->cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? e->C : 1;
+  int t = stage_host(e, X_host, labels_host, batch, ycols, &Xd, &Yd); if (t < 0) return t;
+  if (gen_noise) { int r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }
+  int r = do_cls(e, Xd, Yd, batch, gen_noise ? 1 : 0, keep); if (r) return r;
+  r = release_stage(e, t); if (r) return r;
+  r = e->allreduce_grads(); if (r) return r;
+  r = e->finalize_scalars(batch, false, true); if (r) return r;
+  return e->apply_update(1, batch);
+}
+
+int mmae_forward_host(mmae_engine* e, const float* X_host, const float* target_host, const float* labels_host,
+                      int64_t batch, int use_noise, float keep, uint32_t want, const mmae_outputs* oh) {
+  ENTER(e);
+  if (!X_host) return e->fail(MMAE_ERR_INVALID, "null X");
+  int r = e->ensure_cap(batch); if (r) return r;
+  const int ycols = e->H ? (e->cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? e->C : 1) : 0;
+  float *Xd = nullptr, *Yd = nullptr;
+  int t = stage_host(e, X_host, labels_host, batch, ycols, &Xd, &Yd); if (t < 0) return t;
+  const float* Td = nullptr;
+  cudaError_t ce;
+  if (target_host && target_host != X_host) {      // separate true_X feed: stage it in the other input buffer
+    ce = cudaMemcpyAsync(e->xin[t ^ 1], target_host, (size_t)batch * e->F * 4, cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "H2D target");
+    Td = e->xin[t ^ 1];
+  }
+  // device-side outputs live in engine workspaces, then travel back
+  mmae_outputs od; memset(&od, 0, sizeof(od));
+  if (oh) {
+    if (oh->recon) od.recon = e->out;
+    if (oh->embedding) od.embedding = e->dA;
+    if (oh->logits) od.logits = e->hdelta;
+    if (oh->probs) od.probs = e->hprobs;
+    if (oh->preds) od.preds = e->hpreds;
+    if (oh->filled) od.filled = e->noisy;
+  }
+  r = mmae_forward(e, Xd, Td, labels_host ? Yd : nullptr, batch, use_noise, keep, want, &od); if (r) return r;
+  r = release_stage(e, t); if (r) return r;
+  auto back = [&](void* h, const void* d, size_t bytes) -> cudaError_t {
+    return (h && d) ? cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, e->stream) : cudaSuccess;
+  };
+  ce = cudaSuccess;
+  if (oh) {
+    const size_t pred_count = e->cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? (size_t)batch * e->C : (size_t)batch;
+    if (ce == cudaSuccess && (want & MMAE_WANT_RECON)) ce = back(oh->recon, od.recon, (size_t)batch * e->F * 4);
+    if (ce == cudaSuccess && (want & MMAE_WANT_EMBEDDING)) ce = back(oh->embedding, od.embedding, (size_t)batch * e->E * 4);
+    if (ce == cudaSuccess && (want & MMAE_WANT_FILLED)) ce = back(oh->filled, od.filled, (size_t)batch * e->F * 4);
+    if (ce == cudaSuccess && e->H) ce = back(oh->logits, od.logits, (size_t)batch * e->C * 4);
+    if (ce == cudaSuccess && e->H) ce = back(oh->probs, od.probs, (size_t)batch * e->C * 4);
+    if (ce == cudaSuccess && e->H) ce = back(oh->preds, od.preds, pred_count * 4);
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "D2H outputs");
+  return 0;
+}
+
+int mmae_set_dataset(mmae_engine* e, int slot, const float* X_host, const float* Y_host, int64_t rows, int32_t label_cols) {
+  ENTER(e);
+  if (slot < 0 || slot > 1 || !X_host || rows <= 0) return e->fail(MMAE_ERR_INVALID, "bad dataset arguments");
+  cudaError_t ce = cudaStreamSynchronize(e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "sync");
+  if (e->ds_X[slot]) { cudaFree(e->ds_X[slot]); e->ds_X[slot] = nullptr; }
+  if (e->ds_Y[slot]) { cudaFree(e->ds_Y[slot]); e->ds_Y[slot] = nullptr; }
+  ce = cudaMalloc(&e->ds_X[slot], (size_t)rows * e->F * 4);
+  if (ce == cudaSuccess) ce = cudaMemcpy(e->ds_X[slot], X_host, (size_t)rows * e->F * 4, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess && Y_host && label_cols > 0) {
+    ce = cudaMalloc(&e->ds_Y[slot], (size_t)rows * label_cols * 4);
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->ds_Y[slot], Y_host, (size_t)rows * label_cols * 4, cudaMemcpyHostToDevice);
+  }
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "set_dataset");
+  e->ds_rows[slot] = rows; e->ds_ycols[slot] = (Y_host && label_cols > 0) ? label_cols : 0;
+  return 0;
+}
+
+int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, int64_t batch, int gen_noise, float keep,
+                             int classification) {
+  ENTER(e);
+  if (slot < 0 || slot > 1 || !e->ds_X[slot]) return e->fail(MMAE_ERR_STATE, "dataset slot is empty");
+  if (classification && !e->ds_Y[slot]) return e->fail(MMAE_ERR_STATE, "dataset slot has no labels");
+  int r = e->ensure_cap(batch); if (r) return r;
+  cudaError_t ce;
+  if (idx_host) {
+    ce = cudaMemcpyAsync(e->d_idx, idx_host, (size_t)batch * 8, cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "H2D indices");
+  } else {
+    philox_indices_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, e->stream>>>(e->d_idx, batch, e->first_row,
+                                                                                (uint32_t)e->ds_rows[slot], (uint32_t)e->rng_step, e->cfg.seed);
+    ++e->launches;
+  }
+  const int wpb = 8;
+  gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_X[slot], e->d_idx, e->xin[0], batch, e->F);
+  ++e->launches;
+  if (classification) {
+    gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_Y[slot], e->d_idx, e->yin[0], batch, e->ds_ycols[slot]);
+    ++e->launches;
+  }
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "gather");
+  if (gen_noise) { r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }
+  if (classification) return mmae_cls_train_step(e, e->xin[0], e->yin[0], batch, gen_noise ? 1 : 0, keep);
+  return mmae_train_step(e, e->xin[0], batch, gen_noise ? 1 : 0, keep);
+}
+
+int mmae_read_scalars(mmae_engine* e, double* out, int count) {
+  ENTER(e);
+  if (!out || count <= 0 || count > MMAE_NUM_SCALARS) return e->fail(MMAE_ERR_INVALID, "bad scalar count");
+  cudaError_t ce = cudaMemcpyAsync(out, e->d_scalars, (size_t)count * 8, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "read_scalars");
+  return 0;
+}
+
+int mmae_comm_unique_id(void* id_out_128) {
+  std::string err;
+  if (!id_out_128) return MMAE_ERR_INVALID;
+  if (!load_nccl(err)) { g_create_error = err; return MMAE_ERR_COMM; }
+  int r = g_nccl.GetUniqueId(id_out_128);
+  if (r != 0) { g_create_error = "ncclGetUniqueId failed"; return MMAE_ERR_COMM; }
+  return 0;
+}
+
+int mmae_comm_init(mmae_engine* e, const void* id_128, int rank, int world_size) {
+  ENTER(e);
+  std::string err;
+  if (!load_nccl(err)) return e->fail(MMAE_ERR_COMM, err);
+  Id128 id; memcpy(&id, id_128, 128);
+  int r = g_nccl.CommInitRank(&e->comm, world_size, id, rank);
+  if (r != 0) return e->fail(MMAE_ERR_COMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  e->world = world_size; e->rank = rank;
+  return 0;
+}
+
+int mmae_set_shard(mmae_engine* e, int64_t global_batch, int64_t first_row) {
+  ENTER(e); e->global_batch = global_batch; e->first_row = first_row; return 0;
+}
+
+int64_t mmae_kernel_launches(const mmae_engine* e) { return e ? e->launches : 0; }
+
+int mmae_get_buffer(mmae_engine* e, const char* name, float* host, int64_t count) {
+  ENTER(e);
+  const float* src = nullptr;
+  std::string n = name ? name : "";
+  if (n == "eps") src = e->eps; else if (n == "mu") src = e->mu; else if (n == "lv") src = e->lv;
+  else if (n == "emb") src = e->cur_emb; else if (n == "out") src = e->out; else if (n == "logits") src = e->hlogits;
+  if (!src) return e->fail(MMAE_ERR_NOTFOUND, "unknown or unallocated buffer " + n);
+  cudaError_t ce = cudaStreamSynchronize(e->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpy(host, src, (size_t)count * 4, cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "get_buffer");
+  return 0;
+}
+
+int mmae_set_eps(mmae_engine* e, const float* eps_host, int64_t count) {
+  ENTER(e);
+  if (!e->cfg.variational) return e->fail(MMAE_ERR_STATE, "not variational");
+  if (!eps_host) { e->eps_injected = false; return 0; }
+  int r = e->ensure_cap((count + e->E - 1) / e->E); if (r) return r;
+  cudaError_t ce = cudaStreamSynchronize(e->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpy(e->eps, eps_host, (size_t)count * 4, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "set_eps");
+  e->eps_injected = true;
+  return 0;
+}
+
+int mmae_debug_gemm(int precision, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                    const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, int activation, float beta,
+                    void* stream) {
+  GemmArgs g; memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  g.ep.mode = bias || activation ? EPI_BIAS_ACT : EPI_PLAIN; g.ep.bias = bias; g.ep.act = activation; g.ep.beta = beta; g.ep.keep = 1.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == MMAE_PREC_TF32) {
+    if (!tc_gemm_eligible(transA != 0, transB != 0, g)) return MMAE_ERR_INVALID;
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    TcPlan pl = tc_plan(g, sms, 1);
+    cudaError_t e = launch_gemm_tc(transA != 0, transB != 0, g, pl, nullptr, st);
+    return e == cudaSuccess ? 0 : MMAE_ERR_CUDA;
+  }
+  cudaError_t e = launch_gemm_simt(transA != 0, transB != 0, g, st);
+  return e == cudaSuccess ? 0 : MMAE_ERR_CUDA;
+}
+
+}  // extern "C"

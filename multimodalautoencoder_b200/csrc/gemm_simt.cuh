@@ -1,0 +1,125 @@
+// CUDA-core fp32 GEMM with the fused MMAE prologue (block-mask noise on the X operand) and
+// epilogue (bias / activation / dropout / loss / act').  This is the exact-fp32 family:
+// it serves MMAE_PREC_FP32 engines and every shape the tcgen05 family cannot take
+// (leading dimensions not a multiple of 4 floats, the 2-/3-wide head, batch < 128).
+//
+//   C[M,N] = opA(A) . opB(B),  row-major C;  TA: A stored [K,M];  TB: B stored [N,K].
+//
+// 64x64x16 block tile, 256 threads, 4x4 register tile per thread; every global access is
+// bounds-checked so any M, N, K works (the reference's placeholders are shapeless,
+// multimodal_autoencoder.py:351-352).
+#pragma once
+#include "common.cuh"
+
+namespace mmae {
+
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_THREADS = 256;
+
+struct GemmArgs {
+  int64_t M, N, K;
+  const float* A; int64_t lda;
+  const float* B; int64_t ldb;
+  float* C; int64_t ldc;
+  NoiseView noise;      // applied to A's stored (row, col) = (batch row, feature) when enabled
+  Epilogue ep;
+};
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const GemmArgs g) {
+  __shared__ float As[SG_BK][SG_BM + 4];
+  __shared__ float Bs[SG_BK][SG_BN + 4];
+  __shared__ float red[SG_THREADS / 32];
+
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * SG_BM;     // M tiles on grid.x (no 65535 limit)
+  const int64_t n0 = (int64_t)blockIdx.y * SG_BN;
+  const int tx = tid & 15, ty = tid >> 4;     // 16 x 16 threads; thread owns rows ty*4.., cols tx*4..
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t k0 = 0; k0 < g.K; k0 += SG_BK) {
+    // ---- A tile -> As[k][m]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m, k;
+      if (!TA) { k = tid & 15; m = (tid >> 4) + 16 * i; }     // K contiguous in memory
+      else     { m = tid & 63; k = (tid >> 6) + 4 * i; }      // M contiguous in memory
+      int64_t gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < g.M && gk < g.K) {
+        if (!TA) { v = __ldg(g.A + gm * g.lda + gk); v = noisy_value(g.noise, gm, (int)gk, v); }
+        else     { v = __ldg(g.A + gk * g.lda + gm); v = noisy_value(g.noise, gk, (int)gm, v); }
+      }
+      As[k][m] = v;
+    }
+    // ---- B tile -> Bs[k][n]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int n, k;
+      if (!TB) { n = tid & 63; k = (tid >> 6) + 4 * i; }      // N contiguous
+      else     { k = tid & 15; n = (tid >> 4) + 16 * i; }     // K contiguous
+      int64_t gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < g.N && gk < g.K) v = !TB ? __ldg(g.B + gk * g.ldb + gn) : __ldg(g.B + gn * g.ldb + gk);
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  float loss_acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t r = m0 + ty * 4 + i;
+    if (r >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t c = n0 + tx * 4 + j;
+      if (c >= g.N) continue;
+      float* p = g.C + r * g.ldc + c;
+      float old = (g.ep.beta != 0.f) ? *p : 0.f;
+      *p = epilogue_apply(g.ep, r, c, acc[i][j], old, loss_acc);
+    }
+  }
+  if (g.ep.loss_partials) {             // fixed-order block reduction -> one partial per CTA
+    float w = warp_sum(loss_acc);
+    if ((tid & 31) == 0) red[tid >> 5] = w;
+    __syncthreads();
+    if (tid == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < SG_THREADS / 32; ++i) s += red[i];
+      g.ep.loss_partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+  }
+}
+
+inline int64_t gemm_simt_num_ctas(int64_t M, int64_t N) {
+  return ((M + SG_BM - 1) / SG_BM) * ((N + SG_BN - 1) / SG_BN);
+}
+
+inline cudaError_t launch_gemm_simt(bool ta, bool tb, const GemmArgs& g, cudaStream_t st) {
+  dim3 grid((unsigned)((g.M + SG_BM - 1) / SG_BM), (unsigned)((g.N + SG_BN - 1) / SG_BN));
+  if (grid.y > 65535u) return cudaErrorInvalidConfiguration;
+  if (!ta && !tb) gemm_simt_kernel<false, false><<<grid, SG_THREADS, 0, st>>>(g);
+  else if (!ta && tb) gemm_simt_kernel<false, true><<<grid, SG_THREADS, 0, st>>>(g);
+  else if (ta && !tb) gemm_simt_kernel<true, false><<<grid, SG_THREADS, 0, st>>>(g);
+  else gemm_simt_kernel<true, true><<<grid, SG_THREADS, 0, st>>>(g);
+  return cudaGetLastError();
+}
+
+}  // namespace mmae

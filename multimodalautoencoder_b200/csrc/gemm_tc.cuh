@@ -1,0 +1,153 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a, kind::tf32 (fp32 storage, fp32 accumulation in TMEM).
+//
+//   C[M,N] = opA(A) . opB(B) with the fused MMAE epilogue (common.cuh).
+//   A_MN: A stored [K,M] (M contiguous -> MN-major operand, wgrad);  else [M,K] (K-major).
+//   B_MN: B stored [K,N] (N contiguous -> MN-major operand, y = x.W); else [N,K] (K-major, dgrad / tied).
+//
+// Structure (one CTA per SM, persistent over a static tile schedule):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d -> 128B-swizzled smem ring, mbarrier expect_tx
+//   warp 1      MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8),
+//               tcgen05.commit frees the smem stage / publishes the accumulator
+//   warps 2..5  epilogue: tcgen05.ld 32x32b.x32 (each warp its TMEM lane quadrant), fused
+//               bias/activation/dropout/loss/act', 128-bit global stores
+//   TMEM: 2 accumulator stages x BN fp32 columns, so the epilogue of tile t overlaps the MMAs of t+1.
+// Tails: TMA zero-fills out-of-bounds rows / columns / K; the epilogue bounds-checks its stores.
+// Requirements (checked by tc_gemm_eligible): lda, ldb, ldc multiples of 4 floats, 16-byte aligned bases.
+#pragma once
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"   // GemmArgs
+
+namespace mmae {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                 // 32 fp32 = 128 bytes = one swizzle row
+constexpr int TC_UMMA_K = 8;              // kind::tf32: 32 bytes of K per instruction
+constexpr int TC_THREADS = 192;           // 6 warps
+constexpr int TC_EPI_WARP0 = 2;
+
+template <int BN> struct TcCfg {
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = TC_BM * TC_BK * 4;          // 16 KB
+  static constexpr int kBBytes = BN * TC_BK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;                   // 128 / 256 / 512 (power of two)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TcParams {
+  CUtensorMap tmA, tmB;
+  int64_t M, N, K;
+  float* C; int64_t ldc;
+  int m_blocks, n_blocks, splits;
+  int64_t k_per_split;          // multiple of TC_BK
+  int64_t split_stride;         // elements between split-K slices of C (0 when splits == 1)
+  Epilogue ep;
+};
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map over a row-major [rows, cols] matrix (cols contiguous), 128B swizzle.
+inline bool make_tmap(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, int64_t ld,
+                      int box_cols, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  static int use_tf32_type = -1;     // MMAE_TMA_TF32=0 loads raw fp32 (the MMA then truncates to tf32)
+  if (use_tf32_type < 0) { const char* ev = getenv("MMAE_TMA_TF32"); use_tf32_type = (ev && ev[0] == '0') ? 0 : 1; }
+  CUresult r = enc(tm, use_tf32_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+inline bool tc_gemm_eligible(bool ta, bool tb, const GemmArgs& g) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (g.noise.enabled) return false;                 // the noisy operand is materialised first on this path
+  if ((g.lda & 3) || (g.ldb & 3) || (g.ldc & 3)) return false;
+  if (!al(g.A) || !al(g.B) || !al(g.C)) return false;
+  if (g.M < 128 || g.N < 32 || g.K < 32) return false;
+  if (g.ep.target && (g.ep.ldt & 3)) return false;
+  (void)ta; (void)tb;
+  return true;
+}
+
+inline int tc_pick_bn(int64_t N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }
+
+struct TcPlan { int bn; int m_blocks, n_blocks, splits; int64_t k_per_split; int grid; };
+
+inline TcPlan tc_plan(const GemmArgs& g, int num_sms, int max_splits) {
+  TcPlan pl;
+  pl.bn = tc_pick_bn(g.N);
+  pl.m_blocks = (int)((g.M + TC_BM - 1) / TC_BM);
+  pl.n_blocks = (int)((g.N + pl.bn - 1) / pl.bn);
+  int64_t tiles = (int64_t)pl.m_blocks * pl.n_blocks;
+  int64_t kblocks = (g.K + TC_BK - 1) / TC_BK;
+  int splits = 1;
+  if (max_splits > 1 && tiles < num_sms) {
+    splits = (int)((num_sms + tiles - 1) / tiles);
+    if (splits > max_splits) splits = max_splits;
+    if ((int64_t)splits > kblocks / 8) splits = (int)(kblocks / 8 > 0 ? kblocks / 8 : 1);
+  }
+  int64_t kb_per = (kblocks + splits - 1) / splits;
+  pl.k_per_split = kb_per * TC_BK;
+  pl.splits = (int)((kblocks + kb_per - 1) / kb_per);
+  int64_t total = tiles * pl.splits;
+  pl.grid = (int)(total < num_sms ? total : num_sms);
+  return pl;
+}
+
+// defined in gemm_tc_64.cu / gemm_tc_128.cu / gemm_tc_256.cu (one translation unit per tile width)
+cudaError_t tc_launch_64(bool a_mn, bool b_mn, const TcParams& p, int grid, cudaStream_t st);
+cudaError_t tc_launch_128(bool a_mn, bool b_mn, const TcParams& p, int grid, cudaStream_t st);
+cudaError_t tc_launch_256(bool a_mn, bool b_mn, const TcParams& p, int grid, cudaStream_t st);
+
+// C (or split-K slices in `splitk_ws`) = opA(A) opB(B).  Returns the number of loss partials written
+// (= grid) through *n_partials.  When pl.splits > 1 the caller reduces the slices afterwards.
+inline cudaError_t launch_gemm_tc(bool ta, bool tb, const GemmArgs& g, const TcPlan& pl, float* splitk_ws,
+                                  cudaStream_t st) {
+  TcParams p;
+  const bool a_mn = ta, b_mn = !tb;
+  bool ok = true;
+  if (!a_mn) ok = ok && make_tmap(&p.tmA, g.A, g.M, g.K, g.lda, TC_BK, TC_BM);
+  else       ok = ok && make_tmap(&p.tmA, g.A, g.K, g.M, g.lda, 32, TC_BK);
+  if (!b_mn) ok = ok && make_tmap(&p.tmB, g.B, g.N, g.K, g.ldb, TC_BK, pl.bn);
+  else       ok = ok && make_tmap(&p.tmB, g.B, g.K, g.N, g.ldb, 32, TC_BK);
+  if (!ok) return cudaErrorInvalidValue;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits; p.k_per_split = pl.k_per_split;
+  p.ep = g.ep;
+  if (pl.splits > 1) {
+    p.C = splitk_ws; p.ldc = g.N; p.split_stride = g.M * g.N;
+    p.ep.mode = EPI_PLAIN; p.ep.beta = 0.f; p.ep.loss_partials = nullptr;
+  } else {
+    p.C = g.C; p.ldc = g.ldc; p.split_stride = 0;
+  }
+  if (pl.bn == 256) return tc_launch_256(a_mn, b_mn, p, pl.grid, st);
+  if (pl.bn == 128) return tc_launch_128(a_mn, b_mn, p, pl.grid, st);
+  return tc_launch_64(a_mn, b_mn, p, pl.grid, st);
+}
+
+}  // namespace mmae

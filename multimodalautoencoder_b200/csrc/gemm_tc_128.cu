@@ -1,0 +1,7 @@
+#include "gemm_tc_kernel.cuh"
+
+namespace mmae {
+cudaError_t tc_launch_128(bool a_mn, bool b_mn, const TcParams& p, int grid, cudaStream_t st) {
+  return tc_launch_impl<128>(a_mn, b_mn, p, grid, st);
+}
+}  // namespace mmae

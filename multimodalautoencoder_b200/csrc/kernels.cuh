@@ -1,0 +1,337 @@
+// Streaming / reduction kernels around the GEMMs.  All are HBM-bound: 128-bit accesses where the
+// layout allows, grids sized as a multiple of the SM count, fixed-order (deterministic) reductions.
+// Reference lines cited are in /root/reference/multimodal_autoencoder.py unless a file is named.
+#pragma once
+#include "common.cuh"
+
+namespace mmae {
+
+// ------------------------------------------------------------------ noise descriptor (:668-702)
+// One thread per row draws the row's modality mask; one warp-strided loop draws the n_zero
+// column indices (WITH replacement, :682) and ORs them into the row's bitmap.
+struct NoiseGenArgs {
+  uint32_t* zero_bits; uint32_t* mod_bits;
+  int64_t batch, row0;
+  int num_feats, zw, n_zero, num_mod;
+  int mode, num_types, num_drop;
+  uint32_t thresholds[8]; uint32_t type_masks[8];
+  uint32_t step; uint64_t seed;
+};
+
+__global__ void noise_gen_kernel(const NoiseGenArgs a) {
+  // one warp per row
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= a.batch) return;
+  int64_t grow = row + a.row0;
+  uint32_t* zb = a.zero_bits + row * a.zw;
+  for (int w = lane; w < a.zw; w += 32) zb[w] = 0u;
+  __syncwarp();
+  int q = (a.n_zero + 3) >> 2;                      // Philox counters per row
+  for (int c = lane; c < q; c += 32) {
+    Philox4 p = philox4x32((uint64_t)grow * q + c, kStreamZero, a.step, a.seed);
+    uint32_t wv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      int j = c * 4 + l;
+      if (j < a.n_zero) {
+        uint32_t col = mulhi_u32(wv[l], (uint32_t)a.num_feats);
+        atomicOr(zb + (col >> 5), 1u << (col & 31));
+      }
+    }
+  }
+  if (lane == 0) {
+    Philox4 p = philox4x32((uint64_t)grow, kStreamMod, a.step, a.seed);
+    uint32_t mb = 0u;
+    if (a.mode == MMAE_NOISE_INTELLIGENT) {         // categorical over noise types (:689-695)
+      int k = 0;
+      for (int t = 0; t < a.num_types - 1; ++t) k += (p.x >= a.thresholds[t]) ? 1 : 0;
+      mb = a.type_masks[k];
+    } else {                                        // randint(0, M) num_drop times (:698-700)
+      uint32_t wv[4] = {p.x, p.y, p.z, p.w};
+      for (int d = 0; d < a.num_drop; ++d) mb |= 1u << mulhi_u32(wv[d], (uint32_t)a.num_mod);
+    }
+    a.mod_bits[row] = mb;
+  }
+}
+
+// noisy_X materialised (add_noise_to_batch's return value), float4 where F % 4 == 0
+__global__ void noise_apply_kernel(const float* __restrict__ X, float* __restrict__ out, int64_t batch,
+                                   int num_feats, NoiseView nv) {
+  int64_t total = batch * (int64_t)num_feats;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / num_feats; int c = (int)(i - r * num_feats);
+    out[i] = noisy_value(nv, r, c, __ldg(X + i));
+  }
+}
+
+// ------------------------------------------------------------------ batch gather (data_funcs.py:167-168)
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
+                                   float* __restrict__ dst, int64_t batch, int width) {
+  // one warp per row, float4 when possible
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= batch) return;
+  const float* s = src + idx[row] * (int64_t)width;
+  float* d = dst + row * (int64_t)width;
+  if ((width & 3) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(s); float4* d4 = reinterpret_cast<float4*>(d);
+    for (int i = lane; i < (width >> 2); i += 32) d4[i] = __ldg(s4 + i);
+  } else {
+    for (int i = lane; i < width; i += 32) d[i] = __ldg(s + i);
+  }
+}
+
+__global__ void philox_indices_kernel(int64_t* idx, int64_t batch, int64_t first, uint32_t n_rows,
+                                      uint32_t step, uint64_t seed) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  idx[i] = (int64_t)mulhi_u32(philox_word((uint64_t)(i + first), kStreamBatch, step, seed), n_rows);
+}
+
+// ------------------------------------------------------------------ column sums (bias gradients)
+// stage 1: grid (ceil(N/32), S); block 32x8; partial[s][n] = sum over this split's rows.
+__global__ void colsum_partial_kernel(const float* __restrict__ D, int64_t rows, int n, int64_t ld,
+                                      float* __restrict__ partial, int splits) {
+  __shared__ float sm[8][33];
+  int col = blockIdx.x * 32 + threadIdx.x;
+  int64_t per = (rows + splits - 1) / splits;
+  int64_t r0 = (int64_t)blockIdx.y * per, r1 = min(rows, r0 + per);
+  float s = 0.f;
+  if (col < n)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += __ldg(D + r * ld + col);
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    partial[(int64_t)blockIdx.y * n + col] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int n, int splits, float* __restrict__ out) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= n) return;
+  float t = 0.f;
+  for (int s = 0; s < splits; ++s) t += partial[(int64_t)s * n + col];
+  out[col] = t;
+}
+
+// split-K partial slices -> C (+ beta*C), fixed order
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int64_t mn, int splits, float* __restrict__ C,
+                                     int64_t n, int64_t ldc, float beta) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < mn; i += (int64_t)gridDim.x * blockDim.x) {
+    float t = 0.f;
+    for (int s = 0; s < splits; ++s) t += __ldg(ws + (int64_t)s * mn + i);
+    int64_t r = i / n, c = i - r * n;
+    float* p = C + r * ldc + c;
+    *p = beta != 0.f ? t + beta * (*p) : t;
+  }
+}
+
+// ------------------------------------------------------------------ loss finalisation
+// Sums per-CTA partials in a fixed order (double) and writes scalars; single block.
+// sums[0] = recon loss sum / sumsq, sums[1] = KL sum, ...; see engine.cu for slot use.
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int64_t n, double* __restrict__ out_slot,
+                                       int accumulate) {
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += (double)partials[i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out_slot = accumulate ? (*out_slot + sm[0]) : sm[0];
+}
+
+// ------------------------------------------------------------------ VAE (:372-375, :402-406)
+struct VaeArgs {
+  const float* mu; const float* lv; float* eps; float* emb; float* kl_partials;
+  int64_t batch, row0; int E; uint32_t step; uint64_t seed; int gen_eps;
+};
+__global__ void vae_sample_kernel(const VaeArgs a) {
+  __shared__ float red[8];
+  int64_t total = a.batch * (int64_t)a.E;
+  float kl = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float e;
+    if (a.gen_eps) {
+      Philox4 p = philox4x32((uint64_t)(i + a.row0 * a.E), kStreamEps, a.step, a.seed);
+      float u1 = ((float)(p.x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+      float u2 = (float)(p.y >> 8) * (1.0f / 16777216.0f);
+      e = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+      a.eps[i] = e;
+    } else {
+      e = a.eps[i];
+    }
+    float lv = a.lv[i];
+    float z = a.mu[i] + e * expf(lv);
+    a.emb[i] = z;
+    kl += -0.5f * (1.f + 2.f * lv - z * z - expf(2.f * lv));
+  }
+  float w = warp_sum(kl);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    a.kl_partials[blockIdx.x] = s;
+  }
+}
+// g_mu = g_e + kl_w*emb ; g_lv = g_mu*eps*exp(lv) + kl_w*(exp(2 lv) - 1)      (appendix B)
+// kl_w = 1/B_global on the reconstruction step, 0 on the classification step.
+__global__ void vae_grad_kernel(float* __restrict__ g_e /*in: dL/demb, out: g_mu*/, float* __restrict__ g_lv,
+                                const float* __restrict__ emb, const float* __restrict__ lv,
+                                const float* __restrict__ eps, int64_t total, float kl_w) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float l = lv[i];
+    float g = g_e[i] + kl_w * emb[i];
+    g_e[i] = g;
+    g_lv[i] = g * eps[i] * expf(l) + kl_w * (expf(2.f * l) - 1.f);
+  }
+}
+
+// ------------------------------------------------------------------ head loss (:431-452)
+struct HeadLossArgs {
+  const float* logits; const float* labels; float* delta; float* probs; int32_t* preds;
+  float* partials;      // [gridDim.x * 2]: loss sum, correct count
+  int64_t batch; int C; int loss; float inv_count;   // 1/(B_global*C) or 1/B_global
+};
+__global__ void head_loss_kernel(const HeadLossArgs a) {
+  __shared__ float red[2][8];
+  float ls = 0.f, correct = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.batch; r += (int64_t)gridDim.x * blockDim.x) {
+    const float* l = a.logits + r * a.C;
+    if (a.loss == MMAE_HEAD_SIGMOID_CE) {
+      for (int c = 0; c < a.C; ++c) {
+        float v = l[c], s = sigmoidf_(v);
+        int p = v > 0.f ? 1 : 0;                       // round-half-even(sigmoid) (:448)
+        if (a.probs) a.probs[r * a.C + c] = s;
+        if (a.preds) a.preds[r * a.C + c] = p;
+        if (a.labels) {
+          float y = a.labels[r * a.C + c];
+          ls += fmaxf(v, 0.f) - v * y + log1pf(expf(-fabsf(v)));
+          correct += (p == (int)y) ? 1.f : 0.f;        // tf.cast(float->int32) truncates (:425)
+          if (a.delta) a.delta[r * a.C + c] = (s - y) * a.inv_count;
+        }
+      }
+    } else {
+      float mx = l[0]; int am = 0;
+      for (int c = 1; c < a.C; ++c) if (l[c] > mx) { mx = l[c]; am = c; }
+      float se = 0.f;
+      for (int c = 0; c < a.C; ++c) se += expf(l[c] - mx);
+      if (a.probs) for (int c = 0; c < a.C; ++c) a.probs[r * a.C + c] = sigmoidf_(l[c]);
+      if (a.preds) a.preds[r] = am;                    // argmax (:450)
+      if (a.labels) {
+        int y = (int)a.labels[r];
+        ls += mx + logf(se) - l[y];
+        correct += (am == y) ? 1.f : 0.f;
+        if (a.delta) for (int c = 0; c < a.C; ++c)
+          a.delta[r * a.C + c] = (expf(l[c] - mx) / se - (c == y ? 1.f : 0.f)) * a.inv_count;
+      }
+    }
+  }
+  float w0 = warp_sum(ls), w1 = warp_sum(correct);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = w0; red[1][threadIdx.x >> 5] = w1; }
+  __syncthreads();
+  if (threadIdx.x == 0 && a.partials) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s0 += red[0][i]; s1 += red[1][i]; }
+    a.partials[blockIdx.x] = s0;
+    a.partials[gridDim.x + blockIdx.x] = s1;
+  }
+}
+
+// ------------------------------------------------------------------ fused scale + L2 + TF-Adam (:411, :443)
+// tf.train.AdamOptimizer._apply_dense:  a_t = lr*sqrt(1-b2^t)/(1-b1^t);  m += (g-m)(1-b1);
+// v += (g^2-v)(1-b2);  theta -= a_t * m / (sqrt(v)+eps).   g = scale*G + l2[seg]*theta.
+struct AdamSeg { int64_t begin; float l2; float pad; };
+struct AdamArgs {
+  float* P; const float* G; float* M; float* V;
+  int64_t begin, end;            // flat range inside P / G;  M, V are indexed from 0 at `begin`
+  const AdamSeg* segs; int nsegs;
+  const double* sums;            // device scalars (loss sums after the optional allreduce)
+  int scale_mode;                // 0: 1.0   1: RMSE 1/sqrt(N*sumsq), N = n_elems
+  double n_elems;
+  float alpha, b1, b2, eps;
+  double* scalars_out;           // MMAE_S_* slots, written by thread 0
+};
+__global__ void adam_kernel(const AdamArgs a) {
+  float scale = 1.f;
+  if (a.scale_mode == 1) scale = (float)(1.0 / sqrt(a.n_elems * a.sums[0]));
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.scalars_out) a.scalars_out[MMAE_S_GRAD_SCALE] = scale;
+  int64_t n = a.end - a.begin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t gi = a.begin + i;
+    int lo = 0, hi = a.nsegs - 1;                 // last segment with begin <= gi
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (a.segs[mid].begin <= gi) lo = mid; else hi = mid - 1; }
+    float p = a.P[gi];
+    float g = scale * a.G[gi] + a.segs[lo].l2 * p;
+    float m = a.M[i], v = a.V[i];
+    m += (g - m) * (1.f - a.b1);
+    v += (g * g - v) * (1.f - a.b2);
+    a.M[i] = m; a.V[i] = v;
+    a.P[gi] = p - a.alpha * m / (sqrtf(v) + a.eps);
+  }
+}
+
+// ------------------------------------------------------------------ fill-in (data_funcs.py:310-381)
+// miss[r] bit m set iff sum(x[r, s_m:e_m]) == -(e_m - s_m); one warp per row, lanes stride the block.
+__global__ void missing_bits_kernel(const float* __restrict__ X, int64_t batch, int num_feats,
+                                    const int32_t* __restrict__ starts, int num_mod, uint32_t* __restrict__ miss) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= batch) return;
+  const float* x = X + row * (int64_t)num_feats;
+  uint32_t bits = 0u;
+  for (int m = 0; m < num_mod; ++m) {
+    int s = starts[m], e = starts[m + 1];
+    float t = 0.f;
+    for (int c = s + lane; c < e; c += 32) t += __ldg(x + c);
+    t = warp_sum(t);
+    if (t == -(float)(e - s)) bits |= 1u << m;
+  }
+  if (lane == 0) miss[row] = bits;
+}
+__global__ void fill_select_kernel(const float* __restrict__ X, const float* __restrict__ recon,
+                                   const uint32_t* __restrict__ miss, const uint8_t* __restrict__ col_mod,
+                                   float* __restrict__ out, int64_t batch, int num_feats) {
+  int64_t total = batch * (int64_t)num_feats;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / num_feats; int c = (int)(i - r * num_feats);
+    out[i] = ((__ldg(miss + r) >> __ldg(col_mod + c)) & 1u) ? __ldg(recon + i) : __ldg(X + i);
+  }
+}
+
+// ------------------------------------------------------------------ small glue kernels
+__global__ void elementwise_epilogue_kernel(float* d, int64_t rows, int cols, Epilogue ep) {
+  int64_t total = rows * (int64_t)cols;
+  float dummy = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cols, c = i - r * cols;
+    d[i] = epilogue_apply(ep, r, c, d[i], 0.f, dummy);
+  }
+}
+__global__ void pack_sums_kernel(double* sums, float* tail, int to_tail) {
+  int i = threadIdx.x;
+  if (i < 8) { if (to_tail) tail[i] = (float)sums[i]; else sums[i] = (double)tail[i]; }
+}
+struct FinalizeArgs {
+  const double* sums; double* scalars; int loss; int variational; double n_elems, batch, head_count; int do_recon, do_head;
+};
+__global__ void finalize_scalars_kernel(FinalizeArgs a) {
+  if (a.do_recon) {
+    if (a.loss == MMAE_LOSS_RMSE) { a.scalars[MMAE_S_SUMSQ] = a.sums[0]; a.scalars[MMAE_S_RECON_LOSS] = sqrt(a.sums[0] / a.n_elems); }
+    else { a.scalars[MMAE_S_SUMSQ] = 0.0; a.scalars[MMAE_S_RECON_LOSS] = a.sums[0]; }
+    a.scalars[MMAE_S_KL_MEAN] = a.variational ? a.sums[1] / a.batch : 0.0;
+  }
+  if (a.do_head) {
+    a.scalars[MMAE_S_HEAD_LOSS] = a.sums[2] / a.head_count;
+    a.scalars[MMAE_S_HEAD_ACC] = a.sums[3] / a.head_count;
+  }
+}
+
+}  // namespace mmae

@@ -1,0 +1,318 @@
+"""CUDA engine (through the C ABI) against the fp64 oracle on identical inputs, weights, masks.
+
+Tolerances (SURVEY 8c / north star): masks, indices, predictions bit-exact; fp32 engine <= 1e-5
+relative on losses / reconstructions, <= 1e-4 relative-to-max on gradients; tf32 engine <= 1e-3
+relative on reconstruction loss, <= 5e-3 relative-to-max on reconstructions and gradients.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mmae_oracle as O
+from oracle import philox_host as PH
+from tests.helpers import T_STARTS, S_NAMES, make_cfgs, rel_err, dropout_masks
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'fp32': dict(loss=1e-5, out=2e-5, grad=1e-4, param=2e-5),
+       'tf32': dict(loss=1e-3, out=5e-3, grad=5e-3, param=2e-3)}
+
+
+def _engine(ecfg, P):
+    from multimodalautoencoder_b200 import Engine
+    e = Engine(ecfg)
+    e.set_params({k: v.astype(np.float32) for k, v in P.items()})
+    return e
+
+
+def _data(ocfg, B, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0.0, 1.0, (B, ocfg.num_feats)).astype(np.float32).astype(np.float64)
+    return rng, X
+
+
+# --------------------------------------------------------------------------- noise
+def test_numpy_mode_noise_bit_exact():
+    """rng_mode='numpy': same np.random.seed -> the engine masks exactly the reference's cells."""
+    from multimodalautoencoder_b200.noise import numpy_descriptor, type_masks_from_names
+    ocfg, ecfg = make_cfgs()
+    rng, X = _data(ocfg, 257, 0)
+    P = O.init_params(ocfg, rng)
+    e = _engine(ecfg, P)
+    np.random.seed(11)
+    want = O.add_noise(ocfg, X)                                   # oracle transliteration, global RandomState
+    np.random.seed(11)
+    zb, mb = numpy_descriptor(257, 320, 5, True, ocfg.noise_p, type_masks_from_names(ocfg.noise_types, S_NAMES))
+    e.set_noise(zb, mb)
+    got = e.apply_noise(X.astype(np.float32)).cpu().numpy()
+    assert np.array_equal(got, want.astype(np.float32))
+    # uniform (non-intelligent) mode, two modalities per row
+    ocfg2, ecfg2 = make_cfgs(intelligent=False, num_drop=2)
+    np.random.seed(5)
+    want2 = O.add_noise(ocfg2, X)
+    np.random.seed(5)
+    zb, mb = numpy_descriptor(257, 320, 5, False, num_drop=2)
+    e.set_noise(zb, mb)
+    assert np.array_equal(e.apply_noise(X.astype(np.float32)).cpu().numpy(), want2.astype(np.float32))
+    e.close()
+
+
+@pytest.mark.parametrize('intelligent', [True, False])
+def test_philox_noise_matches_host_twin(intelligent):
+    ocfg, ecfg = make_cfgs(intelligent=intelligent, num_drop=2, seed=0x1234ABCD5678)
+    rng, X = _data(ocfg, 1000, 1)
+    e = _engine(ecfg, O.init_params(ocfg, rng))
+    e.set_rng_step(7)
+    e.gen_noise(1000, first_row=40)
+    zb, mb = e.get_noise(1000)
+    thr = PH.categorical_thresholds(ocfg.noise_p)
+    zb2, mb2 = PH.noise_descriptor(ecfg.seed, 7, 1000, 320, 5, 16, intelligent, thr, e.type_masks, 2, row0=40)
+    assert np.array_equal(zb, zb2) and np.array_equal(mb, mb2)
+    got = e.apply_noise(X.astype(np.float32)).cpu().numpy()
+    assert np.array_equal(got, O.noise_from_descriptor(ocfg, X, zb2, mb2).astype(np.float32))
+    if intelligent:   # distribution sanity: noise-type frequencies follow P (:202)
+        e.gen_noise(1000)
+        freq = np.mean(e.get_noise(1000)[1] == 0)
+        assert abs(freq - 0.64) < 0.06
+    e.close()
+
+
+# --------------------------------------------------------------------------- recon step
+CASES = [
+    dict(id='S-tied-softsign-sce', kw=dict()),
+    dict(id='S-untied-relu-rmse', kw=dict(tie=False, act='relu', loss='mean_squared', lam=0.001)),
+    dict(id='S-tied-tanh-rmse-L3', kw=dict(layers=(128, 64, 32), act='tanh', loss='mean_squared', lam=0.01)),
+    dict(id='S-vae', kw=dict(layers=(128, 64, 32), vae=True, lam=0.001)),
+    dict(id='S-untied-softplus', kw=dict(tie=False, act='softplus', lam=0.01)),
+    dict(id='grid-1000-100', kw=dict(layers=(1000, 100), tie=False, act='relu', lam=0.001)),
+    dict(id='tiny-ragged', kw=dict(num_feats=31, starts=T_STARTS, layers=(12, 6), lam=0.01)),
+    dict(id='one-layer', kw=dict(layers=(64,), loss='mean_squared')),
+    dict(id='linear-ce', kw=dict(act='linear', layers=(64, 32))),
+]
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'tf32'])
+@pytest.mark.parametrize('case', CASES, ids=[c['id'] for c in CASES])
+def test_forward_backward_parity(case, prec):
+    ocfg, ecfg = make_cfgs(precision=prec, **case['kw'])
+    B = 384 if ocfg.num_feats == 320 else 37
+    rng, X = _data(ocfg, B, 2)
+    P = O.init_params(ocfg, rng)
+    e = _engine(ecfg, P)
+    zb, mb = PH.noise_descriptor(0, 0, B, ocfg.num_feats, len(ocfg.modality_names), int(ocfg.num_feats * .05), True,
+                                 PH.categorical_thresholds(ocfg.noise_p), e.type_masks, 1)
+    noisy = O.noise_from_descriptor(ocfg, X, zb, mb)
+    e.set_noise(zb, mb)
+    eps = None
+    if ocfg.variational:
+        eps = rng.standard_normal((B, ocfg.layer_sizes[-1])).astype(np.float32)
+        e.set_eps(eps)
+    tol = TOL[prec]
+    # forward fetches (:945): decoded_X, reconstruction_loss, embedding
+    r = e.forward(X.astype(np.float32), noise=True, recon=True, embedding=True, loss=True)
+    sc = e.scalars()
+    c = O.forward(ocfg, P, noisy, X, eps=eps)
+    assert abs(sc['recon_loss'] - c['recon_loss']) <= tol['loss'] * abs(c['recon_loss'])
+    assert rel_err(r['recon'].cpu().numpy(), c['decoded']) <= tol['out']
+    assert rel_err(r['embedding'].cpu().numpy(), c['emb']) <= tol['out']
+    if ocfg.variational:
+        assert abs(sc['kl_mean'] - np.mean(c['kl'])) <= tol['loss'] * abs(np.mean(c['kl']))
+    # one optimizer step (:590): gradients, then parameters after TF-Adam
+    P2 = {k: v.copy() for k, v in P.items()}
+    st = O.AdamState()
+    c2, G = O.train_step(ocfg, P2, st, noisy, X, eps=eps)
+    e.train_step(X.astype(np.float32), noise=True)
+    sc = e.scalars()
+    assert abs(sc['recon_loss'] - c2['recon_loss']) <= tol['loss'] * abs(c2['recon_loss'])
+    scale = sc['grad_scale'] if ocfg.loss_func == 'mean_squared' else 1.0
+    lam = ocfg.weight_penalty
+    for k, g in G.items():
+        got = e.get_gradient(k).astype(np.float64) * scale
+        l2 = 0.0
+        if k.startswith('weights'):
+            l2 = (2 * lam if ocfg.tie_weights else lam)
+        elif k.startswith('decode_weights') or k == 'variance_weights':
+            l2 = lam
+        got = got + l2 * P[k]                       # the engine folds L2 into Adam, the oracle into G
+        assert rel_err(got, g) <= tol['grad'], (k, rel_err(got, g))
+    for k in G:
+        step = np.abs(P2[k] - P[k]).max()
+        err = np.abs(e.get_variable(k) - P2[k]).max()
+        assert err <= max(tol['param'] * 10 * step, 1e-7), (k, err, step)
+    untouched = set(P) - set(G)
+    for k in untouched:
+        assert np.array_equal(e.get_variable(k), P[k].astype(np.float32)), k
+    e.close()
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'tf32'])
+def test_training_curve_parity(prec):
+    """20 steps of noisy training: loss curve and final parameters follow the oracle."""
+    ocfg, ecfg = make_cfgs(precision=prec, tie=False, lam=0.001, lr=1e-3)
+    B = 256
+    rng, Xall = _data(ocfg, 2048, 3)
+    P = O.init_params(ocfg, rng)
+    e = _engine(ecfg, P)
+    st = O.AdamState()
+    thr = PH.categorical_thresholds(ocfg.noise_p)
+    for step in range(20):
+        idx = PH.batch_indices(0, step, B, 2048)
+        X = Xall[idx]
+        zb, mb = PH.noise_descriptor(0, step, B, 320, 5, 16, True, thr, e.type_masks, 1)
+        noisy = O.noise_from_descriptor(ocfg, X, zb, mb)
+        c, _ = O.train_step(ocfg, P, st, noisy, X)
+        e.set_rng_step(step)
+        e.gen_noise(B)
+        e.train_step(X.astype(np.float32), noise=True)
+        got = e.scalars()['recon_loss']
+        assert abs(got - c['recon_loss']) <= (1e-3 if prec == 'tf32' else 2e-5) * c['recon_loss'], step
+    for k in P:
+        assert rel_err(e.get_variable(k), P[k]) <= (2e-3 if prec == 'tf32' else 1e-4), k
+    e.close()
+
+
+# --------------------------------------------------------------------------- dropout / Philox streams
+@pytest.mark.parametrize('prec', ['fp32', 'tf32'])
+def test_dropout_masks_match_host_twin(prec):
+    ocfg, ecfg = make_cfgs(precision=prec, layers=(128, 64, 32), tie=False, act='relu', lam=0.0, seed=99)
+    B, keep = 256, 0.5
+    rng, X = _data(ocfg, B, 4)
+    P = O.init_params(ocfg, rng)
+    e = _engine(ecfg, P)
+    e.set_rng_step(3)
+    masks = dropout_masks(ocfg, 99, 3, B, keep)
+    P2 = {k: v.copy() for k, v in P.items()}
+    c, G = O.train_step(ocfg, P2, O.AdamState(), X, X, keep=keep, drop_masks=masks)
+    e.train_step(X.astype(np.float32), noise=False, keep=keep)
+    tol = TOL[prec]
+    assert abs(e.scalars()['recon_loss'] - c['recon_loss']) <= tol['loss'] * c['recon_loss']
+    for k, g in G.items():
+        assert rel_err(e.get_gradient(k), g) <= tol['grad'], k
+    e.close()
+
+
+# --------------------------------------------------------------------------- classification head
+HEAD_CASES = [
+    dict(id='C-sigmoid', kw=dict(layers=(200, 100), head=[50, 20], tie=True, act='relu')),
+    dict(id='C-softmax', kw=dict(layers=(200, 100), head=[50, 20], num_labels=None, cls_loss='softmax', tie=False)),
+    dict(id='C-vae', kw=dict(layers=(200, 100), head=[25, 10], vae=True, cls_lam=0.001)),
+    dict(id='C-quirk-deep-ae', kw=dict(layers=(128, 64, 32, 16), head=[10], cls_act='tanh', cls_lam=0.001)),
+]
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'tf32'])
+@pytest.mark.parametrize('case', HEAD_CASES, ids=[c['id'] for c in HEAD_CASES])
+def test_classification_step_parity(case, prec):
+    ocfg, ecfg = make_cfgs(precision=prec, **case['kw'])
+    B = 300
+    rng, X = _data(ocfg, B, 6)
+    P = O.init_params(ocfg, rng)
+    e = _engine(ecfg, P)
+    Y = (rng.uniform(size=(B, 3)) < 0.5).astype(np.float64) if ocfg.num_labels else rng.integers(0, 2, B).astype(np.float64)
+    eps = None
+    if ocfg.variational:
+        eps = rng.standard_normal((B, ocfg.layer_sizes[-1])).astype(np.float32)
+        e.set_eps(eps)
+    tol = TOL[prec]
+    r = e.forward(X.astype(np.float32), labels=Y.astype(np.float32), head=True, head_loss=True)
+    sc = e.scalars()
+    c = O.forward(ocfg, P, X, None, eps=eps, true_Y=Y, want_head=True)
+    assert abs(sc['head_loss'] - c['cls_data_loss']) <= tol['loss'] * 5 * abs(c['cls_data_loss'])
+    assert rel_err(r['logits'].cpu().numpy(), c['cls_logits']) <= tol['out']
+    margin = np.abs(c['cls_logits']).min() if prec == 'tf32' else 0
+    if prec == 'fp32' or margin > 1e-2:
+        assert np.array_equal(r['preds'].cpu().numpy(), c['predictions'])
+        assert abs(sc['head_acc'] - c['accuracy']) < 1e-6
+    P2 = {k: v.copy() for k, v in P.items()}
+    c2, G = O.cls_train_step(ocfg, P2, O.AdamState(), X, Y, eps=eps)
+    e.cls_train_step(X.astype(np.float32), Y.astype(np.float32))
+    for k, g in G.items():
+        got = e.get_gradient(k).astype(np.float64)
+        if k.startswith('classification_weights'):
+            got = got + ocfg.cls_weight_penalty * P[k]
+        assert rel_err(got, g) <= tol['grad'], (k, rel_err(got, g))
+    for k in G:
+        step = np.abs(P2[k] - P[k]).max()
+        assert np.abs(e.get_variable(k) - P2[k]).max() <= max(tol['param'] * 10 * step, 1e-7), k
+    for k in set(P) - set(G):     # decoder variables are not touched by classification_opt_step (:443)
+        assert np.array_equal(e.get_variable(k), P[k].astype(np.float32)), k
+    e.close()
+
+
+# --------------------------------------------------------------------------- inference (:932-950, :1189-1216)
+@pytest.mark.parametrize('prec', ['fp32', 'tf32'])
+def test_fill_in_and_per_modality(prec):
+    ocfg, ecfg = make_cfgs(precision=prec, loss='mean_squared', tie=False)
+    B = 512
+    rng, X = _data(ocfg, B, 8)
+    P = O.init_params(ocfg, rng)
+    e = _engine(ecfg, P)
+    Xm = X.copy()
+    drop = rng.uniform(size=(B, 5)) < 0.2
+    for m in range(5):
+        Xm[drop[:, m], ocfg.modality_starts[m]:ocfg.modality_starts[m + 1]] = -1.0
+    r = e.forward(Xm.astype(np.float32), recon=True, filled=True, loss=True)
+    c = O.forward(ocfg, P, Xm, Xm)
+    want = O.fill_missing(ocfg, Xm, c['decoded'])
+    got = r['filled'].cpu().numpy()
+    keep_mask = np.repeat(~drop, np.diff(ocfg.modality_starts), axis=1)
+    assert np.array_equal(got[keep_mask], Xm.astype(np.float32)[keep_mask])        # untouched cells bit-exact
+    assert rel_err(got, want) <= TOL[prec]['out']
+    assert abs(e.scalars()['recon_loss'] - c['recon_loss']) <= TOL[prec]['loss'] * c['recon_loss']
+    # host-buffer variant of the same call (predict(): NumPy in, NumPy out)
+    rh = e.forward_host(Xm.astype(np.float32), recon=True, filled=True, loss=True)
+    assert np.array_equal(rh['filled'], got) and np.array_equal(rh['recon'], r['recon'].cpu().numpy())
+    e.close()
+
+
+def test_host_step_equals_device_step():
+    ocfg, ecfg = make_cfgs(precision='fp32', head=[50, 20])
+    rng, X = _data(ocfg, 200, 9)
+    P = O.init_params(ocfg, rng)
+    Y = (rng.uniform(size=(200, 3)) < 0.5).astype(np.float32)
+    a, b = _engine(ecfg, P), _engine(ecfg, P)
+    Xf = X.astype(np.float32)
+    for s in range(3):
+        a.set_rng_step(s); b.set_rng_step(s)
+        a.gen_noise(200)
+        a.train_step(Xf, noise=True, keep=0.5)
+        b.train_step_host(Xf, gen_noise=True, keep=0.5)
+        a.cls_train_step(Xf, Y)
+        b.cls_train_step_host(Xf, Y)
+    b.synchronize()
+    for k in P:
+        assert np.array_equal(a.get_variable(k), b.get_variable(k)), k
+    a.close(); b.close()
+
+
+def test_resident_dataset_step():
+    ocfg, ecfg = make_cfgs(precision='fp32')
+    rng, X = _data(ocfg, 1000, 10)
+    P = O.init_params(ocfg, rng)
+    a, b = _engine(ecfg, P), _engine(ecfg, P)
+    a.set_dataset(0, X)
+    a.set_rng_step(5); b.set_rng_step(5)
+    a.train_step_resident(0, 128, idx=None, gen_noise=True)
+    idx = PH.batch_indices(0, 5, 128, 1000)
+    b.gen_noise(128)
+    b.train_step(X[idx].astype(np.float32), noise=True)
+    for k in P:
+        assert np.array_equal(a.get_variable(k), b.get_variable(k)), k
+    a.close(); b.close()
+
+
+def test_errors_are_loud():
+    from multimodalautoencoder_b200 import Engine
+    ocfg, ecfg = make_cfgs()
+    with pytest.raises(ValueError):
+        bad = make_cfgs(layers=(64,), vae=False)[1]
+        bad.variational = True
+        Engine(bad)
+    e = Engine(ecfg)
+    with pytest.raises(ValueError):
+        e.set_variable('no_such_var', np.zeros(3))
+    with pytest.raises(RuntimeError):
+        e.cls_train_step(np.zeros((4, 320), np.float32), np.zeros((4, 3), np.float32))   # no head
+    with pytest.raises(RuntimeError):
+        e.train_step(np.zeros((4, 320), np.float32), noise=True)                         # no descriptor yet
+    e.close()
