@@ -67,8 +67,10 @@ inline PFN_encodeTiled get_encode_fn() {
 }
 
 // 2-D fp32 tensor map over a row-major [rows, cols] matrix (cols contiguous), 128B swizzle.
+// mn_major operands (32-bit elements) must use the 128B swizzle with 32-byte atomicity
+// ("for mn-major tf32 operands, SW128_32B is the only available smem layout").
 inline bool make_tmap(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, int64_t ld,
-                      int box_cols, int box_rows) {
+                      int box_cols, int box_rows, bool mn_major = false) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -78,7 +80,8 @@ inline bool make_tmap(CUtensorMap* tm, const float* base, int64_t rows, int64_t 
   static int use_tf32_type = -1;     // MMAE_TMA_TF32=0 loads raw fp32 (the MMA then truncates to tf32)
   if (use_tf32_type < 0) { const char* ev = getenv("MMAE_TMA_TF32"); use_tf32_type = (ev && ev[0] == '0') ? 0 : 1; }
   CUresult r = enc(tm, use_tf32_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -132,9 +135,9 @@ inline cudaError_t launch_gemm_tc(bool ta, bool tb, const GemmArgs& g, const TcP
   const bool a_mn = ta, b_mn = !tb;
   bool ok = true;
   if (!a_mn) ok = ok && make_tmap(&p.tmA, g.A, g.M, g.K, g.lda, TC_BK, TC_BM);
-  else       ok = ok && make_tmap(&p.tmA, g.A, g.K, g.M, g.lda, 32, TC_BK);
+  else       ok = ok && make_tmap(&p.tmA, g.A, g.K, g.M, g.lda, 32, TC_BK, true);
   if (!b_mn) ok = ok && make_tmap(&p.tmB, g.B, g.N, g.K, g.ldb, TC_BK, pl.bn);
-  else       ok = ok && make_tmap(&p.tmB, g.B, g.K, g.N, g.ldb, 32, TC_BK);
+  else       ok = ok && make_tmap(&p.tmB, g.B, g.K, g.N, g.ldb, 32, TC_BK, true);
   if (!ok) return cudaErrorInvalidValue;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits; p.k_per_split = pl.k_per_split;

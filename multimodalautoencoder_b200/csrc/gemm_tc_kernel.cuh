@@ -59,14 +59,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 shared memory descriptor"), SWIZZLE_128B:
 //   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
-//   [46,48) version = 1, [61,64) layout type = 2 (128-byte swizzle).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   [46,48) version = 1, [61,64) layout type: 2 = 128-byte swizzle (K-major operands),
+//   1 = 128-byte swizzle with 32-byte atomicity (the only legal layout for MN-major 32-bit operands).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -177,9 +179,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
           for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
             // K-major: rows of 128 B, 8-row groups 1024 B apart; advance 32 B per UMMA_K inside the swizzle row.
-            // MN-major: atoms [8 k][32 mn] of 1024 B; MN chunks 4096 B apart (LBO), k groups 1024 B apart (SBO).
-            uint64_t adesc = !A_MN ? make_smem_desc(sa + kk * 32, 16, 1024) : make_smem_desc(sa + kk * 1024, 4096, 1024);
-            uint64_t bdesc = !B_MN ? make_smem_desc(sb + kk * 32, 16, 1024) : make_smem_desc(sb + kk * 1024, 4096, 1024);
+            // MN-major (SW128, 32B atoms): atoms [4 k][32 mn] of 512 B; MN chunks 4096 B apart (LBO), k groups
+            // 512 B apart (SBO); one UMMA_K = 8 spans two k groups = 1024 B.
+            uint64_t adesc = !A_MN ? make_smem_desc(sa + kk * 32, 16, 1024) : make_smem_desc(sa + kk * 1024, 4096, 512, 1);
+            uint64_t bdesc = !B_MN ? make_smem_desc(sb + kk * 32, 16, 1024) : make_smem_desc(sb + kk * 1024, 4096, 512, 1);
             tc_mma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
             accumulate = 1;
           }
