@@ -189,6 +189,10 @@ int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, 
 /* ---- scalars of the last call ---- */
 int mmae_read_scalars(mmae_engine* e, double* out, int count);
 
+/* Same, without synchronising: enqueues the device->host copy on the engine's stream into caller-owned
+ * PINNED memory (the per-step loss read of a training loop that must not stall the pipeline). */
+int mmae_read_scalars_async(mmae_engine* e, double* pinned_host, int count);
+
 /* ---- data parallel: engine-owned NCCL communicator (libnccl is dlopen'ed on first use) ---- */
 int mmae_comm_unique_id(void* id_out_128);
 int mmae_comm_init(mmae_engine* e, const void* id_128, int rank, int world_size);
@@ -199,6 +203,11 @@ int mmae_set_shard(mmae_engine* e, int64_t global_batch, int64_t first_row);
 
 /* ---- introspection used by tests and bench ---- */
 int64_t mmae_kernel_launches(const mmae_engine* e);   /* kernels launched since create */
+/* Device-side timing of the tcgen05 GEMM launches (CUDA events on the engine's stream around each
+ * launch); read returns the accumulated milliseconds, algorithmic FLOPs (2*M*N*K) and launch count
+ * since profiling was switched on. */
+int mmae_set_profiling(mmae_engine* e, int on);
+int mmae_read_profile(mmae_engine* e, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
 int mmae_get_buffer(mmae_engine* e, const char* name, float* host, int64_t count); /* "eps","mu","lv","emb","out","logits" */
 /* Inject the VAE epsilon (tf.random_normal, :374) for parity runs; NULL returns to Philox draws. */
 int mmae_set_eps(mmae_engine* e, const float* eps_host, int64_t count);

@@ -80,6 +80,9 @@ PROTOTYPES = {
     'mmae_comm_init': (_I, [_P, _P, _I, _I]),
     'mmae_set_shard': (_I, [_P, _L, _L]),
     'mmae_kernel_launches': (_L, [_P]),
+    'mmae_set_profiling': (_I, [_P, _I]),
+    'mmae_read_profile': (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_L)]),
+    'mmae_read_scalars_async': (_I, [_P, _P, _I]),
     'mmae_get_buffer': (_I, [_P, C.c_char_p, _P, _L]),
     'mmae_set_eps': (_I, [_P, _P, _L]),
     'mmae_debug_gemm': (_I, [_I, _I, _I, _L, _L, _L, _P, _L, _P, _L, _P, _L, _P, _I, _F, _P]),

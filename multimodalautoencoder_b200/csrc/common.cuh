@@ -53,6 +53,16 @@ __device__ __forceinline__ float act_fwd(int act, float z) {
   }
 }
 
+__device__ __forceinline__ float act_fwd_fast(int act, float z) {
+  switch (act) {
+    case MMAE_ACT_RELU: return fmaxf(z, 0.f);
+    case MMAE_ACT_TANH: { float e = __expf(-2.f * fabsf(z)); float t = __fdividef(1.f - e, 1.f + e); return z >= 0.f ? t : -t; }
+    case MMAE_ACT_SOFTSIGN: return __fdividef(z, 1.f + fabsf(z));
+    case MMAE_ACT_SOFTPLUS: return fmaxf(z, 0.f) + __logf(1.f + __expf(-fabsf(z)));
+    default: return z;
+  }
+}
+
 // act'(z) expressed through the stored output a = act(z)
 __device__ __forceinline__ float act_bwd_from_output(int act, float a) {
   switch (act) {
@@ -117,16 +127,27 @@ struct Epilogue {
   int64_t lds;
 };
 
-// Applies the epilogue to one accumulator; returns the value to store.  `loss_acc` collects
-// the per-thread loss contribution; `c_old` is the current C value (only read when beta != 0).
-__device__ __forceinline__ float epilogue_apply(const Epilogue& ep, int64_t row, int64_t col,
-                                                float acc, float c_old, float& loss_acc) {
+// Which auxiliary matrix the epilogue reads at (row, col): the loss target or the saved activation.
+__device__ __forceinline__ const float* epilogue_aux_ptr(const Epilogue& ep, int64_t* ld) {
+  if (ep.mode == EPI_LOSS_TRAIN || ep.mode == EPI_LOSS_PRED) { *ld = ep.ldt; return ep.target; }
+  if (ep.mode == EPI_DGRAD) { *ld = ep.lds; return ep.saved; }
+  *ld = 0; return nullptr;
+}
+
+// Applies the epilogue to one accumulator; returns the value to store.  The caller supplies the bias
+// value of the column, the auxiliary value (target / saved activation) and the current C value (only
+// meaningful when beta != 0), so that it can hoist and batch those loads; `loss_acc` collects the
+// per-thread loss contribution.  FAST selects hardware-approximate exp/log/divide (tcgen05 family,
+// tf32 tolerance); the CUDA-core fp32 family keeps the accurate forms.
+template <bool FAST = false>
+__device__ __forceinline__ float epilogue_apply(const Epilogue& ep, int64_t row, int64_t col, float acc,
+                                                float bias_v, float aux, float c_old, float& loss_acc) {
   switch (ep.mode) {
     case EPI_PLAIN:
       return ep.beta != 0.f ? acc + ep.beta * c_old : acc;
     case EPI_BIAS_ACT: {
-      float v = acc + (ep.bias ? __ldg(ep.bias + col) : 0.f);
-      v = act_fwd(ep.act, v);
+      float v = acc + bias_v;
+      v = FAST ? act_fwd_fast(ep.act, v) : act_fwd(ep.act, v);
       if (ep.keep < 1.f) {
         uint32_t w = philox_word((uint64_t)(row + ep.row0) * (uint64_t)ep.drop_width + (uint64_t)col, ep.drop_stream, ep.step, ep.seed);
         v = ((w >> 8) < ep.keep_thr) ? v / ep.keep : 0.f;
@@ -135,26 +156,35 @@ __device__ __forceinline__ float epilogue_apply(const Epilogue& ep, int64_t row,
     }
     case EPI_LOSS_TRAIN:
     case EPI_LOSS_PRED: {
-      float l = acc + (ep.bias ? __ldg(ep.bias + col) : 0.f);
-      float x = ep.target ? __ldg(ep.target + row * ep.ldt + col) : 0.f;
+      const float l = acc + bias_v;
+      const float x = aux;
+      const bool has_t = ep.target != nullptr;
       float out;
       if (ep.loss == MMAE_LOSS_SIGMOID_CE) {
-        float s = sigmoidf_(l);
-        if (ep.target) loss_acc += fmaxf(l, 0.f) - l * x + log1pf(expf(-fabsf(l)));
+        float s;
+        if (FAST) {       // one ex2 + one lg2 + one rcp: e = exp(-|l|); sigmoid = (l >= 0 ? 1 : e) / (1 + e)
+          float e = __expf(-fabsf(l));
+          float inv = __fdividef(1.f, 1.f + e);
+          s = l >= 0.f ? inv : e * inv;
+          if (has_t) loss_acc += fmaxf(l, 0.f) - l * x + __logf(1.f + e);
+        } else {
+          s = sigmoidf_(l);
+          if (has_t) loss_acc += fmaxf(l, 0.f) - l * x + log1pf(expf(-fabsf(l)));
+        }
         out = (ep.mode == EPI_LOSS_TRAIN) ? (s - x) : s;
       } else if (ep.loss == MMAE_LOSS_RMSE) {
         float d = l - x;
-        if (ep.target) loss_acc += d * d;
+        if (has_t) loss_acc += d * d;
         out = (ep.mode == EPI_LOSS_TRAIN) ? d : l;      // unscaled; 1/(N*rmse) is applied in Adam
       } else {
-        if (ep.target) loss_acc += -x * logf(l);
+        if (has_t) loss_acc += -x * logf(l);
         out = (ep.mode == EPI_LOSS_TRAIN) ? (-x / l) : l;
       }
       return out;
     }
     case EPI_DGRAD: {
       float g = ep.beta != 0.f ? acc + ep.beta * c_old : acc;
-      float h = __ldg(ep.saved + row * ep.lds + col);
+      float h = aux;
       if (ep.keep < 1.f) {
         uint32_t w = philox_word((uint64_t)(row + ep.row0) * (uint64_t)ep.drop_width + (uint64_t)col, ep.drop_stream, ep.step, ep.seed);
         if ((w >> 8) < ep.keep_thr) { g = g / ep.keep; h = h * ep.keep; } else { return 0.f; }

@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -127,6 +128,34 @@ struct mmae_engine {
   void* comm = nullptr; int world = 1, rank = 0;
 
   int64_t launches = 0;
+
+  // ---- optional per-GEMM device timing (bench.py roofline): CUDA events around every tcgen05 launch
+  bool profiling = false;
+  struct ProfRec { cudaEvent_t a, b; double flops; int64_t m, n, k; int ta, tb, splits; };
+  std::vector<ProfRec> prof_recs; size_t prof_used = 0;
+  double prof_ms = 0.0, prof_flops = 0.0; int64_t prof_count = 0;
+  int prof_begin(double flops) {
+    if (!profiling) return -1;
+    if (prof_used == prof_recs.size()) {
+      ProfRec r; cudaEventCreate(&r.a); cudaEventCreate(&r.b); r.flops = 0; prof_recs.push_back(r);
+    }
+    prof_recs[prof_used].flops = flops;
+    cudaEventRecord(prof_recs[prof_used].a, stream);
+    return (int)prof_used++;
+  }
+  void prof_end(int i) { if (i >= 0) cudaEventRecord(prof_recs[i].b, stream); }
+  void prof_collect() {
+    cudaStreamSynchronize(stream);
+    for (size_t i = 0; i < prof_used; ++i) {
+      float ms = 0.f; cudaEventElapsedTime(&ms, prof_recs[i].a, prof_recs[i].b);
+      prof_ms += ms; prof_flops += prof_recs[i].flops; ++prof_count;
+      if (getenv("MMAE_PROFILE_DUMP"))
+        fprintf(stderr, "[mmae gemm] M=%lld N=%lld K=%lld ta=%d tb=%d splits=%d  %.3f ms  %.1f TFLOP/s\n",
+                (long long)prof_recs[i].m, (long long)prof_recs[i].n, (long long)prof_recs[i].k, prof_recs[i].ta,
+                prof_recs[i].tb, prof_recs[i].splits, ms, prof_recs[i].flops / (ms * 1e9));
+    }
+    prof_used = 0;
+  }
 
   // ================================================================= helpers
   int fail(int code, const std::string& m) { err = m; if (code == MMAE_ERR_CUDA) sticky = code; return code; }
@@ -320,6 +349,7 @@ struct mmae_engine {
     fr(mu); fr(lv); fr(eps); fr(emb); fr(glv); fr(out); fr(dA); fr(dB);
     fr(hlogits); fr(hdelta); fr(hprobs); fr(hpreds); fr(partials); fr(colsum_ws); fr(splitk_ws); fr(d_idx);
     for (int i = 0; i < 2; ++i) { if (xin_free[i]) cudaEventDestroy(xin_free[i]); if (xin_ready[i]) cudaEventDestroy(xin_ready[i]); }
+    for (auto& r : prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
   }
@@ -334,7 +364,10 @@ struct mmae_engine {
     if (cfg.precision == MMAE_PREC_TF32 && tc_gemm_eligible(ta, tb, g)) {
       TcPlan pl = tc_plan(g, num_sms, allow_splitk && ep.mode == EPI_PLAIN ? 64 : 1);
       if (pl.splits > 1) RET(ensure_splitk((int64_t)pl.splits * m * n));
+      int pr = prof_begin(2.0 * (double)m * (double)n * (double)k);
+      if (pr >= 0) { auto& R = prof_recs[pr]; R.m = m; R.n = n; R.k = k; R.ta = ta; R.tb = tb; R.splits = pl.splits; }
       cudaError_t e = launch_gemm_tc(ta, tb, g, pl, splitk_ws, stream);
+      prof_end(pr);
       ++launches;
       if (e != cudaSuccess) return cuda_fail(e, "tcgen05 gemm launch");
       if (pl.splits > 1) {
@@ -1078,6 +1111,31 @@ int mmae_set_shard(mmae_engine* e, int64_t global_batch, int64_t first_row) {
 }
 
 int64_t mmae_kernel_launches(const mmae_engine* e) { return e ? e->launches : 0; }
+
+int mmae_set_profiling(mmae_engine* e, int on) {
+  ENTER(e);
+  if (e->profiling) e->prof_collect();
+  e->profiling = on != 0;
+  if (on) { e->prof_ms = 0.0; e->prof_flops = 0.0; e->prof_count = 0; }
+  return 0;
+}
+
+int mmae_read_profile(mmae_engine* e, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
+  ENTER(e);
+  e->prof_collect();
+  if (gemm_ms) *gemm_ms = e->prof_ms;
+  if (gemm_flops) *gemm_flops = e->prof_flops;
+  if (gemm_launches) *gemm_launches = e->prof_count;
+  return 0;
+}
+
+int mmae_read_scalars_async(mmae_engine* e, double* pinned_host, int count) {
+  ENTER(e);
+  if (!pinned_host || count <= 0 || count > MMAE_NUM_SCALARS) return e->fail(MMAE_ERR_INVALID, "bad scalar count");
+  cudaError_t ce = cudaMemcpyAsync(pinned_host, e->d_scalars, (size_t)count * 8, cudaMemcpyDeviceToHost, e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "read_scalars_async");
+  return 0;
+}
 
 int mmae_get_buffer(mmae_engine* e, const char* name, float* host, int64_t count) {
   ENTER(e);

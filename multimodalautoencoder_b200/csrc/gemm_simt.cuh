@@ -82,6 +82,13 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const GemmArgs g)
   }
 
   float loss_acc = 0.f;
+  int64_t ldaux; const float* auxp = epilogue_aux_ptr(g.ep, &ldaux);
+  float bias_v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int64_t c = n0 + tx * 4 + j;
+    bias_v[j] = (g.ep.bias && c < g.N) ? __ldg(g.ep.bias + c) : 0.f;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int64_t r = m0 + ty * 4 + i;
@@ -92,7 +99,8 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const GemmArgs g)
       if (c >= g.N) continue;
       float* p = g.C + r * g.ldc + c;
       float old = (g.ep.beta != 0.f) ? *p : 0.f;
-      *p = epilogue_apply(g.ep, r, c, acc[i][j], old, loss_acc);
+      float aux = auxp ? __ldg(auxp + r * ldaux + c) : 0.f;
+      *p = epilogue_apply<false>(g.ep, r, c, acc[i][j], bias_v[j], aux, old, loss_acc);
     }
   }
   if (g.ep.loss_partials) {             // fixed-order block reduction -> one partial per CTA

@@ -8,8 +8,10 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d -> 128B-swizzled smem ring, mbarrier expect_tx
 //   warp 1      MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8),
 //               tcgen05.commit frees the smem stage / publishes the accumulator
-//   warps 2..5  epilogue: tcgen05.ld 32x32b.x32 (each warp its TMEM lane quadrant), fused
-//               bias/activation/dropout/loss/act', 128-bit global stores
+//   warps 2..9  epilogue: tcgen05.ld 32x32b.x32 (two warps per TMEM lane quadrant, alternating 32-column
+//               chunks), transposed through a padded smem staging tile so that every global access of the
+//               fused bias/activation/dropout/loss/act' epilogue (C, target, saved activations) is a
+//               coalesced 128-byte row segment
 //   TMEM: 2 accumulator stages x BN fp32 columns, so the epilogue of tile t overlaps the MMAs of t+1.
 // Tails: TMA zero-fills out-of-bounds rows / columns / K; the epilogue bounds-checks its stores.
 // Requirements (checked by tc_gemm_eligible): lda, ldb, ldc multiples of 4 floats, 16-byte aligned bases.
@@ -25,7 +27,9 @@ namespace mmae {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                 // 32 fp32 = 128 bytes = one swizzle row
 constexpr int TC_UMMA_K = 8;              // kind::tf32: 32 bytes of K per instruction
-constexpr int TC_THREADS = 192;           // 6 warps
+constexpr int TC_THREADS = 320;           // 10 warps: TMA, MMA, 8 epilogue
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_STAGE_LD = 33;           // epilogue staging row stride (floats): conflict-free both ways
 constexpr int TC_EPI_WARP0 = 2;
 
 template <int BN> struct TcCfg {
@@ -34,7 +38,8 @@ template <int BN> struct TcCfg {
   static constexpr int kBBytes = BN * TC_BK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;                   // 128 / 256 / 512 (power of two)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiBytes = TC_EPI_WARPS * 32 * TC_STAGE_LD * 4;   // 33 792 B
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct TcParams {
@@ -91,7 +96,7 @@ inline bool tc_gemm_eligible(bool ta, bool tb, const GemmArgs& g) {
   if (g.noise.enabled) return false;                 // the noisy operand is materialised first on this path
   if ((g.lda & 3) || (g.ldb & 3) || (g.ldc & 3)) return false;
   if (!al(g.A) || !al(g.B) || !al(g.C)) return false;
-  if (g.M < 128 || g.N < 32 || g.K < 32) return false;
+  if (g.M < 128 || g.N < 32 || g.K < 32 || (g.N & 3)) return false;
   if (g.ep.target && (g.ep.ldt & 3)) return false;
   (void)ta; (void)tb;
   return true;

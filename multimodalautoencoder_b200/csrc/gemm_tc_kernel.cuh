@@ -80,6 +80,128 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+
+// ------------------------------------------------------------------ epilogue row loops
+// One lane = one output column; the warp walks the (up to 32) rows of its staged chunk.  Specialised on
+// mode / activation / loss / dropout so the hot loop is ~10-30 instructions per row instead of a generic
+// switch, with pointer-increment addressing and the auxiliary reads (target / saved activation / old C)
+// batched 8 rows ahead.
+template <int ACT> __device__ __forceinline__ float act_fast_t(float z) {
+  if (ACT == MMAE_ACT_RELU) return fmaxf(z, 0.f);
+  if (ACT == MMAE_ACT_TANH) { float e = __expf(-2.f * fabsf(z)); float t = __fdividef(1.f - e, 1.f + e); return z >= 0.f ? t : -t; }
+  if (ACT == MMAE_ACT_SOFTSIGN) return __fdividef(z, 1.f + fabsf(z));
+  if (ACT == MMAE_ACT_SOFTPLUS) return fmaxf(z, 0.f) + __logf(1.f + __expf(-fabsf(z)));
+  return z;
+}
+template <int ACT> __device__ __forceinline__ float dact_t(float a) {
+  if (ACT == MMAE_ACT_RELU) return a > 0.f ? 1.f : 0.f;
+  if (ACT == MMAE_ACT_TANH) return 1.f - a * a;
+  if (ACT == MMAE_ACT_SOFTSIGN) { float t = 1.f - fabsf(a); return t * t; }
+  if (ACT == MMAE_ACT_SOFTPLUS) return 1.f - __expf(-a);
+  return 1.f;
+}
+
+struct EpiRowCtx {
+  float* cp;            // &C[row0, col]
+  const float* ap;      // &aux[row0, col] or null
+  int64_t ldc, ldaux;
+  const float* stg;     // staging + lane (row stride TC_STAGE_LD)
+  int nrows;            // rows of this chunk inside M (warp-uniform)
+  float bias_v, beta;
+  int64_t grow0, col;   // global row (for the dropout stream) and column
+};
+
+// MODE: EpiMode; SUB: activation (BIAS_ACT / DGRAD) or loss (LOSS_*); DROP: dropout enabled
+template <int MODE, int SUB, bool DROP>
+__device__ __forceinline__ void epi_rows(const Epilogue& ep, const EpiRowCtx& c, float& loss_acc) {
+  constexpr bool kAux = (MODE == EPI_LOSS_TRAIN || MODE == EPI_LOSS_PRED || MODE == EPI_DGRAD);
+  const bool use_old = (MODE == EPI_PLAIN || MODE == EPI_DGRAD) && c.beta != 0.f;
+  const bool has_aux = kAux && c.ap != nullptr;
+  float* cp = c.cp; const float* ap = c.ap; const float* sp = c.stg;
+  constexpr int RB = kAux ? 16 : 8;        // rows per batch: 16 x 128 B per warp in flight for the aux stream
+  for (int i0 = 0; i0 < c.nrows; i0 += RB) {
+    float aux[RB], old[RB];
+    const int n = min(RB, c.nrows - i0);
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      aux[u] = (has_aux && u < n) ? __ldg(ap + (int64_t)u * c.ldaux) : 0.f;
+      old[u] = (use_old && u < n) ? cp[(int64_t)u * c.ldc] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      if (u < n) {
+        const float acc = sp[u * TC_STAGE_LD];
+        float out;
+        if (MODE == EPI_PLAIN) {
+          out = acc + c.beta * old[u];
+        } else if (MODE == EPI_BIAS_ACT) {
+          out = act_fast_t<SUB>(acc + c.bias_v);
+          if (DROP) {
+            uint32_t w = philox_word((uint64_t)(c.grow0 + i0 + u) * (uint64_t)ep.drop_width + (uint64_t)c.col, ep.drop_stream, ep.step, ep.seed);
+            out = ((w >> 8) < ep.keep_thr) ? out / ep.keep : 0.f;
+          }
+        } else if (MODE == EPI_DGRAD) {
+          float g = acc + c.beta * old[u];
+          float h = aux[u];
+          if (DROP) {
+            uint32_t w = philox_word((uint64_t)(c.grow0 + i0 + u) * (uint64_t)ep.drop_width + (uint64_t)c.col, ep.drop_stream, ep.step, ep.seed);
+            if ((w >> 8) < ep.keep_thr) { g = g / ep.keep; h = h * ep.keep; } else { g = 0.f; }
+          }
+          out = g * dact_t<SUB>(h);
+        } else {   // EPI_LOSS_TRAIN / EPI_LOSS_PRED, SUB = loss
+          const float l = acc + c.bias_v, x = aux[u];
+          if (SUB == MMAE_LOSS_SIGMOID_CE) {
+            const float e = __expf(-fabsf(l));
+            const float inv = __fdividef(1.f, 1.f + e);
+            const float s = l >= 0.f ? inv : e * inv;
+            if (has_aux) loss_acc += fmaxf(l, 0.f) - l * x + __logf(1.f + e);
+            out = (MODE == EPI_LOSS_TRAIN) ? (s - x) : s;
+          } else if (SUB == MMAE_LOSS_RMSE) {
+            const float d = l - x;
+            if (has_aux) loss_acc += d * d;
+            out = (MODE == EPI_LOSS_TRAIN) ? d : l;
+          } else {
+            if (has_aux) loss_acc += -x * __logf(l);
+            out = (MODE == EPI_LOSS_TRAIN) ? __fdividef(-x, l) : l;
+          }
+        }
+        cp[(int64_t)u * c.ldc] = out;
+      }
+    }
+    cp += RB * c.ldc; sp += RB * TC_STAGE_LD;
+    if (kAux) ap += RB * c.ldaux;
+  }
+}
+
+template <int MODE, bool DROP>
+__device__ __forceinline__ void epi_rows_act(const Epilogue& ep, const EpiRowCtx& c, float& loss_acc) {
+  switch (ep.act) {
+    case MMAE_ACT_RELU: epi_rows<MODE, MMAE_ACT_RELU, DROP>(ep, c, loss_acc); break;
+    case MMAE_ACT_TANH: epi_rows<MODE, MMAE_ACT_TANH, DROP>(ep, c, loss_acc); break;
+    case MMAE_ACT_SOFTSIGN: epi_rows<MODE, MMAE_ACT_SOFTSIGN, DROP>(ep, c, loss_acc); break;
+    case MMAE_ACT_SOFTPLUS: epi_rows<MODE, MMAE_ACT_SOFTPLUS, DROP>(ep, c, loss_acc); break;
+    default: epi_rows<MODE, MMAE_ACT_LINEAR, DROP>(ep, c, loss_acc); break;
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void epi_rows_loss(const Epilogue& ep, const EpiRowCtx& c, float& loss_acc) {
+  switch (ep.loss) {
+    case MMAE_LOSS_SIGMOID_CE: epi_rows<MODE, MMAE_LOSS_SIGMOID_CE, false>(ep, c, loss_acc); break;
+    case MMAE_LOSS_RMSE: epi_rows<MODE, MMAE_LOSS_RMSE, false>(ep, c, loss_acc); break;
+    default: epi_rows<MODE, MMAE_LOSS_CE, false>(ep, c, loss_acc); break;
+  }
+}
+__device__ __forceinline__ void epi_dispatch(const Epilogue& ep, const EpiRowCtx& c, float& loss_acc) {
+  const bool drop = ep.keep < 1.f;
+  switch (ep.mode) {
+    case EPI_PLAIN: epi_rows<EPI_PLAIN, 0, false>(ep, c, loss_acc); break;
+    case EPI_BIAS_ACT: if (drop) epi_rows_act<EPI_BIAS_ACT, true>(ep, c, loss_acc); else epi_rows_act<EPI_BIAS_ACT, false>(ep, c, loss_acc); break;
+    case EPI_DGRAD: if (drop) epi_rows_act<EPI_DGRAD, true>(ep, c, loss_acc); else epi_rows_act<EPI_DGRAD, false>(ep, c, loss_acc); break;
+    case EPI_LOSS_TRAIN: epi_rows_loss<EPI_LOSS_TRAIN>(ep, c, loss_acc); break;
+    default: epi_rows_loss<EPI_LOSS_PRED>(ep, c, loss_acc); break;
+  }
+}
+
 // ------------------------------------------------------------------ the kernel
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
@@ -92,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;      // [2]
   uint64_t* tempty_bar = bars + 2 * Cfg::kStages + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
-  __shared__ float epi_red[4];
+  __shared__ float epi_red[TC_EPI_WARPS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tiles_mn = (int64_t)p.m_blocks * p.n_blocks;
@@ -104,7 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {   // TMEM allocation (this warp also frees it)
@@ -195,56 +317,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       __syncwarp();
     }
   } else {
-    // ===================== epilogue warps =====================
+    // ===================== epilogue warps (8): quadrant = warp % 4, two warps per quadrant =====================
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = (warp - TC_EPI_WARP0) >> 2;     // which of the two warps of the quadrant
+    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + (warp - TC_EPI_WARP0) * 32 * TC_STAGE_LD;
     float loss_acc = 0.f;
+    int64_t ldaux; const float* auxp = epilogue_aux_ptr(p.ep, &ldaux);
     int64_t it = 0;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       int mb, nb, sp; decode(t, mb, nb, sp);
       const int as = (int)(it & 1); const uint32_t aphase = (uint32_t)((it >> 1) & 1);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int64_t row = (int64_t)mb * TC_BM + quad * 32 + lane;
-      float* crow = p.C + (int64_t)sp * p.split_stride + row * p.ldc;
+      const int64_t row0 = (int64_t)mb * TC_BM + quad * 32;
+      float* cbase = p.C + (int64_t)sp * p.split_stride;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = half; ch < BN / 32; ch += 2) {
         uint32_t r[32];
         tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + ch * 32), r);
-        const int64_t col0 = (int64_t)nb * BN + ch * 32;
-        if (row < p.M && col0 < p.N) {
-          if (vec_ok && col0 + 32 <= p.N) {
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.ep.beta != 0.f) o = *reinterpret_cast<const float4*>(crow + col0 + v * 4);
-              o.x = epilogue_apply(p.ep, row, col0 + v * 4 + 0, __uint_as_float(r[v * 4 + 0]), o.x, loss_acc);
-              o.y = epilogue_apply(p.ep, row, col0 + v * 4 + 1, __uint_as_float(r[v * 4 + 1]), o.y, loss_acc);
-              o.z = epilogue_apply(p.ep, row, col0 + v * 4 + 2, __uint_as_float(r[v * 4 + 2]), o.z, loss_acc);
-              o.w = epilogue_apply(p.ep, row, col0 + v * 4 + 3, __uint_as_float(r[v * 4 + 3]), o.w, loss_acc);
-              *reinterpret_cast<float4*>(crow + col0 + v * 4) = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (col0 + j < p.N) {
-                float old = (p.ep.beta != 0.f) ? crow[col0 + j] : 0.f;
-                crow[col0 + j] = epilogue_apply(p.ep, row, col0 + j, __uint_as_float(r[j]), old, loss_acc);
-              }
-            }
-          }
+        for (int j = 0; j < 32; ++j) stg[lane * TC_STAGE_LD + j] = __uint_as_float(r[j]);   // lane = row
+        __syncwarp();
+        const int64_t col = (int64_t)nb * BN + ch * 32 + lane;                               // lane = column
+        if (col < p.N && row0 < p.M) {
+          EpiRowCtx c;
+          c.cp = cbase + row0 * p.ldc + col;
+          c.ap = auxp ? auxp + row0 * ldaux + col : nullptr;
+          c.ldc = p.ldc; c.ldaux = ldaux; c.stg = stg + lane;
+          c.nrows = (int)min((int64_t)32, p.M - row0);
+          c.bias_v = p.ep.bias ? __ldg(p.ep.bias + col) : 0.f;
+          c.beta = p.ep.beta; c.grow0 = row0 + p.ep.row0; c.col = col;
+          epi_dispatch(p.ep, c, loss_acc);
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);    // 4 arrivals (one per epilogue warp) free the accumulator
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);    // 8 arrivals (one per epilogue warp) free the accumulator
     }
     if (p.ep.loss_partials) {
       float w = warp_sum(loss_acc);
-      if (lane == 0) epi_red[quad] = w;
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-      if (warp == TC_EPI_WARP0 && lane == 0)
-        p.ep.loss_partials[blockIdx.x] = epi_red[0] + epi_red[1] + epi_red[2] + epi_red[3];
+      if (lane == 0) epi_red[warp - TC_EPI_WARP0] = w;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
+      if (warp == TC_EPI_WARP0 && lane == 0) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < TC_EPI_WARPS; ++i) sacc += epi_red[i];
+        p.ep.loss_partials[blockIdx.x] = sacc;
+      }
     }
   }
 

@@ -310,9 +310,11 @@ __global__ void fill_select_kernel(const float* __restrict__ X, const float* __r
 __global__ void elementwise_epilogue_kernel(float* d, int64_t rows, int cols, Epilogue ep) {
   int64_t total = rows * (int64_t)cols;
   float dummy = 0.f;
+  int64_t ldaux; const float* auxp = epilogue_aux_ptr(ep, &ldaux);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / cols, c = i - r * cols;
-    d[i] = epilogue_apply(ep, r, c, d[i], 0.f, dummy);
+    float aux = auxp ? auxp[r * ldaux + c] : 0.f;
+    d[i] = epilogue_apply<false>(ep, r, c, d[i], 0.f, aux, 0.f, dummy);
   }
 }
 __global__ void pack_sums_kernel(double* sums, float* tail, int to_tail) {

@@ -405,6 +405,18 @@ class Engine:
             raise EngineError('mmae_comm_unique_id failed: ' + lib.mmae_last_error(None).decode())
         return buf.raw
 
+    def set_profiling(self, on):
+        self._ck(self.lib.mmae_set_profiling(self._h, int(bool(on))))
+
+    def read_profile(self):
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        self._ck(self.lib.mmae_read_profile(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
+        return {'gemm_ms': ms.value, 'gemm_flops': fl.value, 'gemm_launches': n.value}
+
+    def read_scalars_async(self, pinned):
+        """pinned: torch pinned CPU float64 tensor with >= 8 elements."""
+        self._ck(self.lib.mmae_read_scalars_async(self._h, C.c_void_p(pinned.data_ptr()), capi.NUM_SCALARS))
+
     @property
     def kernel_launches(self):
         return self.lib.mmae_kernel_launches(self._h)

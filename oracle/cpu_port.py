@@ -1,0 +1,90 @@
+"""CPU port of the reference's training step, used ONLY as bench.py's cpu_baseline / --impl reference arm.
+TEST/BENCH INFRASTRUCTURE -- NOT PRODUCT CODE.
+
+The reference's own implementation (TensorFlow 1.x graph driven from Python 2) cannot run in this image
+(no TensorFlow, no network), so kind = "port": the same op sequence TensorFlow's CPU
+kernels would execute for session.run([opt_step]) (multimodal_autoencoder.py:590) -- fp32 matmul + bias +
+activation per layer (:454-518), the loss (:381-390), reverse-mode gradients, TF-formula Adam (:411) --
+on torch's multithreaded CPU kernels, preceded by the reference's per-row NumPy noise loop (:668-702),
+which is part of every reference training step (:568-569).
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from . import mmae_oracle as O
+
+
+class CpuPort:
+    def __init__(self, cfg: O.OracleConfig, params, threads=None):
+        if threads:
+            torch.set_num_threads(threads)
+        self.cfg = cfg
+        self.P = {k: torch.tensor(v, dtype=torch.float32, requires_grad=True) for k, v in params.items()}
+        self.m = {k: torch.zeros_like(v) for k, v in self.P.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in self.P.items()}
+        self.t = 0
+
+    def _act(self, z):
+        a = self.cfg.activation
+        if a == 'relu':
+            return torch.relu(z)
+        if a == 'tanh':
+            return torch.tanh(z)
+        if a == 'softsign':
+            return torch.nn.functional.softsign(z)
+        if a == 'softplus':
+            return torch.nn.functional.softplus(z)
+        return z
+
+    def loss(self, noisy, X):
+        cfg, P = self.cfg, self.P
+        h = noisy
+        for i in range(cfg.L):
+            h = h @ P['weights%d' % i] + P['encode_biases%d' % i]
+            if i < cfg.L - 1:
+                h = self._act(h)
+        for j in range(cfg.L):
+            i = cfg.L - 1 - j
+            W = P['weights%d' % i].t() if cfg.tie_weights else P['decode_weights%d' % i]
+            h = h @ W + P['decode_biases%d' % i]
+            if j < cfg.L - 1:
+                h = self._act(h)
+        if cfg.loss_func == 'mean_squared':
+            rec = torch.sqrt(torch.mean((h - X) ** 2))
+        else:
+            rec = torch.nn.functional.binary_cross_entropy_with_logits(h, X, reduction='sum')
+        reg = 0.0
+        if cfg.weight_penalty:
+            for k, w in P.items():
+                if 'weights' in k:
+                    reg = reg + (2.0 if (cfg.tie_weights and k.startswith('weights')) else 1.0) * 0.5 * (w ** 2).sum()
+        return rec + cfg.weight_penalty * reg, rec
+
+    def step(self, X64, rng=np.random, with_noise=True):
+        """One reference training step on a float64 batch (the DataLoader's dtype): noise loop, f64->f32
+        feed cast (:351-352), forward, backward, Adam.  Returns (loss, seconds in the noise loop)."""
+        t0 = time.perf_counter()
+        noisy64 = O.add_noise(self.cfg, X64, rng) if with_noise else X64
+        t_noise = time.perf_counter() - t0
+        X = torch.from_numpy(np.asarray(X64, np.float32))
+        noisy = torch.from_numpy(np.asarray(noisy64, np.float32))
+        total, rec = self.loss(noisy, X)
+        for p in self.P.values():
+            p.grad = None
+        total.backward()
+        self.t += 1
+        c = self.cfg
+        a = c.learning_rate * np.sqrt(1 - c.beta2 ** self.t) / (1 - c.beta1 ** self.t)
+        with torch.no_grad():
+            for k, p in self.P.items():
+                if p.grad is None:
+                    continue
+                g = p.grad
+                self.m[k] += (g - self.m[k]) * (1 - c.beta1)
+                self.v[k] += (g * g - self.v[k]) * (1 - c.beta2)
+                p -= a * self.m[k] / (torch.sqrt(self.v[k]) + c.adam_eps)
+        return float(rec), t_noise
