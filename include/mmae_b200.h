@@ -156,6 +156,11 @@ int mmae_forward(mmae_engine* e, const float* X_dev, const float* target_dev, co
 
 /* ---- session.run([opt_step]) (:590): forward + backward + Adam on the autoencoder ---- */
 int mmae_train_step(mmae_engine* e, const float* X_dev, int64_t batch, int use_noise, float keep);
+/* Same step with the two feeds given separately, as feed_dict {noisy_X: ..., true_X: ...} does (:570-571):
+ * X_in_dev is what the encoder reads (an already-noised matrix when use_noise == 0), target_dev what the
+ * loss compares against. */
+int mmae_train_step_pair(mmae_engine* e, const float* X_in_dev, const float* target_dev, int64_t batch,
+                         int use_noise, float keep);
 /* ---- session.run([classification_opt_step]) (:647) ---- */
 int mmae_cls_train_step(mmae_engine* e, const float* X_dev, const float* labels_dev, int64_t batch,
                         int use_noise, float keep);

@@ -66,6 +66,7 @@ PROTOTYPES = {
     'mmae_apply_noise': (_I, [_P, _P, _L, _P]),
     'mmae_forward': (_I, [_P, _P, _P, _P, _L, _I, _F, _U, C.POINTER(Outputs)]),
     'mmae_train_step': (_I, [_P, _P, _L, _I, _F]),
+    'mmae_train_step_pair': (_I, [_P, _P, _P, _L, _I, _F]),
     'mmae_cls_train_step': (_I, [_P, _P, _P, _L, _I, _F]),
     'mmae_train_step_host': (_I, [_P, _P, _L, _I, _F]),
     'mmae_cls_train_step_host': (_I, [_P, _P, _P, _L, _I, _F]),

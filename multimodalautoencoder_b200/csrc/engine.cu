@@ -688,9 +688,9 @@ int launch_noise_gen(mmae_engine* e, int64_t batch, int64_t first_row) {
   return 0;
 }
 
-int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float keep) {
+int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float keep, const float* target = nullptr) {
   int r = e->begin_step(B, use_noise != 0); if (r) return r;
-  mmae_engine::FwdOpts o; o.X = X; o.target = X; o.labels = nullptr; o.B = B; o.noise = use_noise != 0; o.keep = keep;
+  mmae_engine::FwdOpts o; o.X = X; o.target = target ? target : X; o.labels = nullptr; o.B = B; o.noise = use_noise != 0; o.keep = keep;
   o.train_recon = true; o.decoder = true; o.headp = false; o.recon_out = nullptr;
   r = e->forward(o); if (r) return r;
   r = e->backward_recon(B, keep); if (r) return r;
@@ -946,6 +946,14 @@ int mmae_apply_update(mmae_engine* e, int optimizer) {
 int mmae_train_step(mmae_engine* e, const float* X_dev, int64_t batch, int use_noise, float keep) {
   ENTER(e);
   int r = do_train(e, X_dev, batch, use_noise, keep); if (r) return r;
+  r = e->allreduce_grads(); if (r) return r;
+  r = e->finalize_scalars(batch, true, false); if (r) return r;
+  return e->apply_update(0, batch);
+}
+
+int mmae_train_step_pair(mmae_engine* e, const float* X_in_dev, const float* target_dev, int64_t batch, int use_noise, float keep) {
+  ENTER(e);
+  int r = do_train(e, X_in_dev, batch, use_noise, keep, target_dev); if (r) return r;
   r = e->allreduce_grads(); if (r) return r;
   r = e->finalize_scalars(batch, true, false); if (r) return r;
   return e->apply_update(0, batch);

@@ -277,6 +277,12 @@ class Engine:
         X = self._dev(X)
         self._ck(self.lib.mmae_train_step(self._h, C.c_void_p(X.data_ptr()), X.shape[0], int(bool(noise)), float(keep)))
 
+    def train_step_pair(self, X_in, target, noise=False, keep=1.0):
+        X_in = self._dev(X_in)
+        target = self._dev(target)
+        self._ck(self.lib.mmae_train_step_pair(self._h, C.c_void_p(X_in.data_ptr()), C.c_void_p(target.data_ptr()),
+                                               X_in.shape[0], int(bool(noise)), float(keep)))
+
     def cls_train_step(self, X, Y, noise=False, keep=1.0):
         X = self._dev(X)
         Y = self._dev(Y)
