@@ -122,6 +122,7 @@ struct Epilogue {
   int64_t ldt;
   int loss;               // mmae_loss
   float* loss_partials;   // one float per CTA (deterministic two-stage reduction), may be null
+  float* colsum_partials; // tcgen05 family only: [ceil(M/32), N] column sums of the stored values per 32-row group
   // dgrad mode
   const float* saved;     // stored activations h = drop(act(z)), [M, lds]
   int64_t lds;

@@ -83,6 +83,9 @@ struct mmae_engine {
   std::vector<Var> vars;
   int64_t nP = 0, enc_begin = 0, enc_end = 0;     // group boundaries in the flat buffer
   float *P = nullptr, *G = nullptr;               // G has 8 extra floats: the loss sums (allreduced with it)
+  float* PT = nullptr;                            // K-major (transposed) shadows of the 2-D weights, same offsets
+  std::vector<char> pt_dirty;                     // per variable
+  float* colpart = nullptr; int64_t colpart_cap = 0;   // fused column-sum partials [ceil(M/32), N]
   float *M0 = nullptr, *V0 = nullptr, *M1 = nullptr, *V1 = nullptr;
   int64_t t_opt[2] = {0, 0};
   AdamSeg* d_segs[2] = {nullptr, nullptr};
@@ -269,6 +272,8 @@ struct mmae_engine {
 
     CK(cudaMalloc(&P, nP * 4)); CK(cudaMemset(P, 0, nP * 4));
     CK(cudaMalloc(&G, (nP + 8) * 4)); CK(cudaMemset(G, 0, (nP + 8) * 4));
+    CK(cudaMalloc(&PT, nP * 4)); CK(cudaMemset(PT, 0, nP * 4));
+    pt_dirty.assign(vars.size(), 1);
     CK(cudaMalloc(&M0, enc_end * 4)); CK(cudaMemset(M0, 0, enc_end * 4));
     CK(cudaMalloc(&V0, enc_end * 4)); CK(cudaMemset(V0, 0, enc_end * 4));
     if (H > 0) {
@@ -329,6 +334,8 @@ struct mmae_engine {
     if (pc > partials_cap) { RET(realloc_dev(partials, pc)); partials_cap = pc; }
     int64_t cs = (int64_t)64 * std::max(F, maxw);
     if (cs > colsum_cap) { RET(realloc_dev(colsum_ws, cs)); colsum_cap = cs; }
+    int64_t cpn = ((nc + 31) / 32) * (int64_t)std::max(F, maxw);
+    if (cpn > colpart_cap) { RET(realloc_dev(colpart, cpn)); colpart_cap = cpn; }
     cap = nc;
     return 0;
   }
@@ -341,7 +348,7 @@ struct mmae_engine {
 
   void release() {
     auto fr = [](void* p) { if (p) cudaFree(p); };
-    fr(P); fr(G); fr(M0); fr(V0); fr(M1); fr(V1); fr(d_scalars); fr(d_sums); fr(d_segs[0]); fr(d_segs[1]);
+    fr(PT); fr(colpart); fr(P); fr(G); fr(M0); fr(V0); fr(M1); fr(V1); fr(d_scalars); fr(d_sums); fr(d_segs[0]); fr(d_segs[1]);
     fr(d_col_mod); fr(d_starts); fr(zero_bits); fr(mod_bits); fr(miss_bits);
     for (int i = 0; i < 2; ++i) { fr(xin[i]); fr(yin[i]); fr(ds_X[i]); fr(ds_Y[i]); }
     fr(noisy);
@@ -354,6 +361,28 @@ struct mmae_engine {
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
   }
 
+  // K-major shadow of a weight variable (refreshed lazily after set_variable / Adam); null if w is not a variable
+  const float* shadowT(const float* w, int64_t rows, int64_t cols) {
+    for (size_t i = 0; i < vars.size(); ++i) {
+      Var& v = vars[i];
+      if (P + v.off != w || v.cols == 0 || v.rows != rows || v.cols != cols) continue;
+      if (pt_dirty[i]) {
+        dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+        transpose_kernel<<<grid, block, 0, stream>>>(w, PT + v.off, (int)rows, (int)cols);
+        ++launches;
+        if (cudaGetLastError() != cudaSuccess) return nullptr;
+        pt_dirty[i] = 0;
+      }
+      return PT + v.off;
+    }
+    return nullptr;
+  }
+  void mark_dirty(int64_t begin, int64_t end) {
+    for (size_t i = 0; i < vars.size(); ++i) if (vars[i].off >= begin && vars[i].off < end) pt_dirty[i] = 1;
+  }
+  bool last_gemm_tc = false;
+  bool d_fused = false;      // the current delta's column-sum partials are valid in colpart
+
   // ================================================================= GEMM dispatch
   // C = opA(A) opB(B) with epilogue.  n_partials receives the number of loss partials written.
   int gemm(bool ta, bool tb, int64_t m, int64_t n, int64_t k, const float* A, int64_t lda, const float* B,
@@ -361,7 +390,13 @@ struct mmae_engine {
            bool allow_splitk) {
     GemmArgs g; g.M = m; g.N = n; g.K = k; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = Cp; g.ldc = ldc;
     g.noise = nv; g.ep = ep;
+    last_gemm_tc = false;
     if (cfg.precision == MMAE_PREC_TF32 && tc_gemm_eligible(ta, tb, g)) {
+      last_gemm_tc = true;
+      if (!tb && (k & 3) == 0) {      // y = x.W with W stored [K,N]: use its K-major shadow W^T [N,K] when W is a variable
+        const float* wt = shadowT(B, k, n);
+        if (wt) { g.B = wt; g.ldb = k; tb = true; }
+      }
       TcPlan pl = tc_plan(g, num_sms, allow_splitk && ep.mode == EPI_PLAIN ? 64 : 1);
       if (pl.splits > 1) RET(ensure_splitk((int64_t)pl.splits * m * n));
       int pr = prof_begin(2.0 * (double)m * (double)n * (double)k);
@@ -377,6 +412,7 @@ struct mmae_engine {
       if (n_partials) *n_partials = pl.grid;
       return 0;
     }
+    g.ep.colsum_partials = nullptr;
     cudaError_t e = launch_gemm_simt(ta, tb, g, stream);
     ++launches;
     if (e != cudaSuccess) return cuda_fail(e, "simt gemm launch");
@@ -392,6 +428,13 @@ struct mmae_engine {
     colsum_final_kernel<<<(n + 127) / 128, 128, 0, stream>>>(colsum_ws, n, splits, outp);
     CKL("colsum_final");
     return 0;
+  }
+
+  // db = column sums of delta [rows, n].  `fused` says the GEMM that produced delta already left per-32-row
+  // partial sums in colpart (tcgen05 epilogue), so only ceil(rows/32) partial rows are read instead of delta.
+  int bias_grad(const float* D, int64_t rows, int n, int64_t ld, float* outp, bool fused) {
+    if (fused) return colsum(colpart, (rows + 31) / 32, n, n, outp);
+    return colsum(D, rows, n, ld, outp);
   }
 
   int reduce_partials(int64_t n, int slot, bool accumulate = false) {
@@ -476,8 +519,10 @@ struct mmae_engine {
         } else {
           e = epi(o.train_recon ? EPI_LOSS_TRAIN : EPI_LOSS_PRED); e.bias = pvar(bn); e.loss = cfg.loss_func;
           e.target = o.target; e.ldt = F; e.loss_partials = o.target ? partials : nullptr;
+          if (o.train_recon) e.colsum_partials = colpart;
           dst = o.recon_out ? o.recon_out : out;
           RET(gemm(false, tb, B, dout, din, u, ldu, W, ldw, dst, dout, noise_view(false), e, &np, false));
+          d_fused = o.train_recon && last_gemm_tc;
           if (o.target) RET(reduce_partials(np, 0));
         }
         u = dst; ldu = dout;
@@ -528,21 +573,24 @@ struct mmae_engine {
       char wn[32], bn[32]; snprintf(wn, 32, "weights%d", i); snprintf(bn, 32, "encode_biases%d", i);
       const float* a_in = i == 0 ? x_eff : ea[i - 1];
       NoiseView nv = i == 0 ? x_noise : noise_view(false);
-      RET(colsum(d, B, dout, dout, gvar(bn)));
+      RET(bias_grad(d, B, dout, dout, gvar(bn), d_fused));
       Epilogue ew = epi(EPI_PLAIN); ew.beta = (cfg.tie_weights && !cls_pass) ? 1.f : 0.f;   // tied: decoder part already there
       RET(gemm(true, false, din, dout, B, a_in, din, d, dout, gvar(wn), dout, nv, ew, nullptr, true));
       if (i == 0) break;
       const bool var_here = cfg.variational && i == L - 1;
       Epilogue ed = epi(var_here ? EPI_PLAIN : EPI_DGRAD);
-      if (!var_here) { ed.saved = ea[i - 1]; ed.lds = din; ed.act = cfg.activation; if (keep < 1.f) set_dropout(ed, keep, (uint32_t)(i - 1), din); }
+      if (!var_here) { ed.saved = ea[i - 1]; ed.lds = din; ed.act = cfg.activation; if (keep < 1.f) set_dropout(ed, keep, (uint32_t)(i - 1), din); ed.colsum_partials = colpart; }
       RET(gemm(false, true, B, din, dout, d, dout, pvar(wn), dout, other, din, noise_view(false), ed, nullptr, false));
+      d_fused = !var_here && last_gemm_tc;
       if (var_here) {
         RET(colsum(glv, B, E, E, gvar("variance_bias")));
         Epilogue ev = epi(EPI_PLAIN);
         RET(gemm(true, false, din, E, B, a_in, din, glv, E, gvar("variance_weights"), E, noise_view(false), ev, nullptr, true));
         Epilogue e2 = epi(EPI_DGRAD); e2.beta = 1.f; e2.saved = ea[i - 1]; e2.lds = din; e2.act = cfg.activation;
         if (keep < 1.f) set_dropout(e2, keep, (uint32_t)(i - 1), din);
+        e2.colsum_partials = colpart;
         RET(gemm(false, true, B, din, E, glv, E, pvar("variance_weights"), E, other, din, noise_view(false), e2, nullptr, false));
+        d_fused = last_gemm_tc;
       }
       std::swap(d, other);
     }
@@ -559,7 +607,7 @@ struct mmae_engine {
       const int din = layers[i], dout = enc_in(i);     // decoder layer maps din -> dout
       char wn[32], bn[32]; snprintf(bn, 32, "decode_biases%d", i);
       const float* u_in = j == 0 ? cur_emb : da[j - 1];
-      RET(colsum(d, B, dout, ldd, gvar(bn)));
+      RET(bias_grad(d, B, dout, ldd, gvar(bn), d_fused));
       Epilogue ew = epi(EPI_PLAIN);
       if (cfg.tie_weights) {   // (dD)^T = delta^T . u accumulates into the tied encoder variable
         snprintf(wn, 32, "weights%d", i);
@@ -570,20 +618,24 @@ struct mmae_engine {
       }
       Epilogue ed = epi(j > 0 ? EPI_DGRAD : EPI_PLAIN);
       if (j > 0) { ed.saved = da[j - 1]; ed.lds = din; ed.act = cfg.activation; if (keep < 1.f) set_dropout(ed, keep, 32u + (uint32_t)(j - 1), din); }
+      ed.colsum_partials = colpart;
       // g_u = delta . D^T : untied D stored [din, dout] = [N, K] -> transposed B operand; tied D^T = W_i stored [dout, din] = [K, N]
       RET(gemm(false, !cfg.tie_weights, B, din, dout, d, ldd, pvar(wn), cfg.tie_weights ? din : dout, nxt, din,
                noise_view(false), ed, nullptr, false));
+      d_fused = last_gemm_tc;
       d = nxt; ldd = din; nxt = (nxt == dA) ? dB : dA;
     }
     if (cfg.variational) {
       vae_grad_kernel<<<grid_for(B * E, 256), 256, 0, stream>>>(d, glv, emb, lv, eps, B * E, (float)(1.0 / (double)gbatch(B)));
       CKL("vae_grad");
+      d_fused = false;      // g_mu differs from the stored g_e
     }
     return backward_encoder(B, d, keep);
   }
 
   int backward_cls(int64_t B, float keep) {
     cls_pass = true;
+    d_fused = false;
     float* d = hdelta; int64_t ldd = C;
     float* nxt = dA;
     if (H - 1 < L - 1) {     // quirk (:533): the logits themselves went through act + dropout
@@ -597,18 +649,21 @@ struct mmae_engine {
       const int din = i == 0 ? E : head[i - 1], dout = head[i];
       char wn[40], bn[40]; snprintf(wn, 40, "classification_weights%d", i); snprintf(bn, 40, "classification_biases%d", i);
       const float* u_in = i == 0 ? cur_emb : ha[i - 1];
-      RET(colsum(d, B, dout, ldd, gvar(bn)));
+      RET(bias_grad(d, B, dout, ldd, gvar(bn), d_fused));
       Epilogue ew = epi(EPI_PLAIN);
       RET(gemm(true, false, din, dout, B, u_in, din, d, ldd, gvar(wn), dout, noise_view(false), ew, nullptr, true));
       const bool act_prev = i > 0 && (i - 1) < L - 1;
       Epilogue ed = epi(act_prev ? EPI_DGRAD : EPI_PLAIN);
       if (act_prev) { ed.saved = ha[i - 1]; ed.lds = din; ed.act = cfg.head_activation; if (keep < 1.f) set_dropout(ed, keep, 64u + (uint32_t)(i - 1), din); }
+      ed.colsum_partials = colpart;
       RET(gemm(false, true, B, din, dout, d, ldd, pvar(wn), dout, nxt, din, noise_view(false), ed, nullptr, false));
+      d_fused = last_gemm_tc;
       d = nxt; ldd = din; nxt = (nxt == dA) ? dB : dA;
     }
     if (cfg.variational) {
       vae_grad_kernel<<<grid_for(B * E, 256), 256, 0, stream>>>(d, glv, emb, lv, eps, B * E, 0.f);
       CKL("vae_grad");
+      d_fused = false;
     }
     return backward_encoder(B, d, keep);
   }
@@ -651,6 +706,7 @@ struct mmae_engine {
     a.b1 = cfg.beta1; a.b2 = cfg.beta2; a.eps = cfg.adam_eps; a.scalars_out = d_scalars;
     adam_kernel<<<grid_for(a.end - a.begin, 256), 256, 0, stream>>>(a);
     CKL("adam");
+    mark_dirty(a.begin, a.end);
     return 0;
   }
   int64_t last_B = 0;
@@ -792,7 +848,10 @@ static int var_copy(mmae_engine* e, const char* name, float* base, int64_t base_
 }
 
 int mmae_set_variable(mmae_engine* e, const char* name, const float* host, int64_t count) {
-  ENTER(e); return var_copy(e, name, e->P, 0, const_cast<float*>(host), count, true);
+  ENTER(e);
+  int r = var_copy(e, name, e->P, 0, const_cast<float*>(host), count, true);
+  if (r == 0) e->mark_dirty(0, e->nP);
+  return r;
 }
 int mmae_get_variable(mmae_engine* e, const char* name, float* host, int64_t count) {
   ENTER(e); return var_copy(e, name, e->P, 0, host, count, false);

@@ -109,6 +109,7 @@ struct EpiRowCtx {
   int nrows;            // rows of this chunk inside M (warp-uniform)
   float bias_v, beta;
   int64_t grow0, col;   // global row (for the dropout stream) and column
+  float* colsum_out;    // where this lane's column sum over the chunk's rows goes (null = not wanted)
 };
 
 // MODE: EpiMode; SUB: activation (BIAS_ACT / DGRAD) or loss (LOSS_*); DROP: dropout enabled
@@ -118,6 +119,7 @@ __device__ __forceinline__ void epi_rows(const Epilogue& ep, const EpiRowCtx& c,
   const bool use_old = (MODE == EPI_PLAIN || MODE == EPI_DGRAD) && c.beta != 0.f;
   const bool has_aux = kAux && c.ap != nullptr;
   float* cp = c.cp; const float* ap = c.ap; const float* sp = c.stg;
+  float csum = 0.f;
   constexpr int RB = kAux ? 16 : 8;        // rows per batch: 16 x 128 B per warp in flight for the aux stream
   for (int i0 = 0; i0 < c.nrows; i0 += RB) {
     float aux[RB], old[RB];
@@ -166,11 +168,13 @@ __device__ __forceinline__ void epi_rows(const Epilogue& ep, const EpiRowCtx& c,
           }
         }
         cp[(int64_t)u * c.ldc] = out;
+        csum += out;
       }
     }
     cp += RB * c.ldc; sp += RB * TC_STAGE_LD;
     if (kAux) ap += RB * c.ldaux;
   }
+  if (c.colsum_out) *c.colsum_out = csum;      // fixed row order -> deterministic
 }
 
 template <int MODE, bool DROP>
@@ -347,6 +351,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           c.nrows = (int)min((int64_t)32, p.M - row0);
           c.bias_v = p.ep.bias ? __ldg(p.ep.bias + col) : 0.f;
           c.beta = p.ep.beta; c.grow0 = row0 + p.ep.row0; c.col = col;
+          c.colsum_out = p.ep.colsum_partials ? p.ep.colsum_partials + (row0 >> 5) * p.N + col : nullptr;
           epi_dispatch(p.ep, c, loss_acc);
         }
         __syncwarp();

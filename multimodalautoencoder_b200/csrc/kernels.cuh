@@ -55,14 +55,50 @@ __global__ void noise_gen_kernel(const NoiseGenArgs a) {
   }
 }
 
-// noisy_X materialised (add_noise_to_batch's return value), float4 where F % 4 == 0
+// noisy_X materialised (add_noise_to_batch's return value).  One warp per row: the row's bitmap words and modality
+// mask are read once, X streams through as float4 (F % 4 == 0) with 128-bit coalesced accesses.
 __global__ void noise_apply_kernel(const float* __restrict__ X, float* __restrict__ out, int64_t batch,
                                    int num_feats, NoiseView nv) {
-  int64_t total = batch * (int64_t)num_feats;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / num_feats; int c = (int)(i - r * num_feats);
-    out[i] = noisy_value(nv, r, c, __ldg(X + i));
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < batch; r += nwarps) {
+    const float* x = X + r * (int64_t)num_feats;
+    float* o = out + r * (int64_t)num_feats;
+    const uint32_t mb = nv.enabled ? __ldg(nv.mod_bits + r) : 0u;
+    const uint32_t* zb = nv.zero_bits + r * nv.zw;
+    if ((num_feats & 3) == 0) {
+      for (int c4 = lane; c4 < (num_feats >> 2); c4 += 32) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(x) + c4);
+        const int c = c4 << 2;
+        if (nv.enabled) {
+          const uint32_t z = __ldg(zb + (c >> 5)) >> (c & 31);
+          const uchar4 m = *reinterpret_cast<const uchar4*>(nv.col_mod + c);
+          v.x = ((mb >> m.x) & 1u) ? nv.mask_with : ((z & 1u) ? 0.f : v.x);
+          v.y = ((mb >> m.y) & 1u) ? nv.mask_with : ((z & 2u) ? 0.f : v.y);
+          v.z = ((mb >> m.z) & 1u) ? nv.mask_with : ((z & 4u) ? 0.f : v.z);
+          v.w = ((mb >> m.w) & 1u) ? nv.mask_with : ((z & 8u) ? 0.f : v.w);
+        }
+        reinterpret_cast<float4*>(o)[c4] = v;
+      }
+    } else {
+      for (int c = lane; c < num_feats; c += 32) o[c] = noisy_value(nv, r, c, __ldg(x + c));
+    }
+  }
+}
+
+// out[c][r] = in[r][c]  (K-major shadows of the weights for the tcgen05 forward GEMMs)
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < rows && c < cols) ? __ldg(in + (int64_t)r * cols + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(int64_t)c * rows + r] = t[threadIdx.x][i];
   }
 }
 
