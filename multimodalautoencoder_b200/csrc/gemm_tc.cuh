@@ -49,6 +49,7 @@ struct TcParams {
   int m_blocks, n_blocks, splits;
   int64_t k_per_split;          // multiple of TC_BK
   int64_t split_stride;         // elements between split-K slices of C (0 when splits == 1)
+  int a3d, b3d;                 // MN-major operand loaded through a 3-D map (one TMA per stage)
   Epilogue ep;
 };
 
@@ -91,6 +92,24 @@ inline bool make_tmap(CUtensorMap* tm, const float* base, int64_t rows, int64_t 
   return r == CUDA_SUCCESS;
 }
 
+// 3-D view of an MN-major operand stored [K rows, MN cols]: (32 mn, K, MN/32 chunks) so that ONE TMA instruction
+// lands all 32-column chunks of a stage ([chunk][k][32] in smem, 128B swizzle with 32-byte atoms).  Needs MN % 32 == 0.
+inline bool make_tmap_mn3d(CUtensorMap* tm, const float* base, int64_t k_rows, int64_t mn, int64_t ld, int box_k,
+                           int box_chunks) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  static int use_tf32_type = -1;
+  if (use_tf32_type < 0) { const char* ev = getenv("MMAE_TMA_TF32"); use_tf32_type = (ev && ev[0] == '0') ? 0 : 1; }
+  cuuint64_t dims[3] = {32, (cuuint64_t)k_rows, (cuuint64_t)(mn / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_k, (cuuint32_t)box_chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, use_tf32_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 inline bool tc_gemm_eligible(bool ta, bool tb, const GemmArgs& g) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (g.noise.enabled) return false;                 // the noisy operand is materialised first on this path
@@ -113,11 +132,18 @@ inline TcPlan tc_plan(const GemmArgs& g, int num_sms, int max_splits) {
   pl.n_blocks = (int)((g.N + pl.bn - 1) / pl.bn);
   int64_t tiles = (int64_t)pl.m_blocks * pl.n_blocks;
   int64_t kblocks = (g.K + TC_BK - 1) / TC_BK;
+  // split-K (wgrad only): pick the split count that best fills whole waves of the persistent grid, keeping at
+  // least 32 k-blocks per split and preferring fewer splits when the gain is below 3 % (slices cost HBM traffic)
   int splits = 1;
-  if (max_splits > 1 && tiles < num_sms) {
-    splits = (int)((num_sms + tiles - 1) / tiles);
-    if (splits > max_splits) splits = max_splits;
-    if ((int64_t)splits > kblocks / 8) splits = (int)(kblocks / 8 > 0 ? kblocks / 8 : 1);
+  if (max_splits > 1) {
+    double best = 0.0;
+    for (int s = 1; s <= max_splits; ++s) {
+      if (s > 1 && kblocks / s < 32) break;
+      const int64_t total = tiles * s;
+      const int64_t waves = (total + num_sms - 1) / num_sms;
+      const double eff = (double)total / (double)(waves * num_sms);
+      if (eff > best + 0.03) { best = eff; splits = s; }
+    }
   }
   int64_t kb_per = (kblocks + splits - 1) / splits;
   pl.k_per_split = kb_per * TC_BK;
@@ -139,9 +165,15 @@ inline cudaError_t launch_gemm_tc(bool ta, bool tb, const GemmArgs& g, const TcP
   TcParams p;
   const bool a_mn = ta, b_mn = !tb;
   bool ok = true;
+  static int use3d = -1;
+  if (use3d < 0) { const char* ev = getenv("MMAE_TMA_3D"); use3d = (ev && ev[0] == '0') ? 0 : 1; }
+  p.a3d = (use3d && a_mn && (g.M % 32) == 0) ? 1 : 0;
+  p.b3d = (use3d && b_mn && (g.N % 32) == 0) ? 1 : 0;
   if (!a_mn) ok = ok && make_tmap(&p.tmA, g.A, g.M, g.K, g.lda, TC_BK, TC_BM);
+  else if (p.a3d) ok = ok && make_tmap_mn3d(&p.tmA, g.A, g.K, g.M, g.lda, TC_BK, TC_BM / 32);
   else       ok = ok && make_tmap(&p.tmA, g.A, g.K, g.M, g.lda, 32, TC_BK, true);
   if (!b_mn) ok = ok && make_tmap(&p.tmB, g.B, g.N, g.K, g.ldb, TC_BK, pl.bn);
+  else if (p.b3d) ok = ok && make_tmap_mn3d(&p.tmB, g.B, g.K, g.N, g.ldb, TC_BK, pl.bn / 32);
   else       ok = ok && make_tmap(&p.tmB, g.B, g.K, g.N, g.ldb, 32, TC_BK, true);
   if (!ok) return cudaErrorInvalidValue;
   p.M = g.M; p.N = g.N; p.K = g.K;

@@ -32,6 +32,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -265,6 +270,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (!A_MN) {
             tma_load_2d(&p.tmA, &full_bar[stage], sa, (int)k, mb * TC_BM);            // box {32 k, 128 m}
+          } else if (p.a3d) {
+            tma_load_3d(&p.tmA, &full_bar[stage], sa, 0, (int)k, mb * (TC_BM / 32));    // box {32 m, 32 k, 4 chunks}
           } else {
 #pragma unroll
             for (int c = 0; c < TC_BM / 32; ++c)                                        // box {32 m, 32 k}
@@ -272,6 +279,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           }
           if (!B_MN) {
             tma_load_2d(&p.tmB, &full_bar[stage], sb, (int)k, nb * BN);               // box {32 k, BN n}
+          } else if (p.b3d) {
+            tma_load_3d(&p.tmB, &full_bar[stage], sb, 0, (int)k, nb * (BN / 32));       // box {32 n, 32 k, BN/32 chunks}
           } else {
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c)                                           // box {32 n, 32 k}
