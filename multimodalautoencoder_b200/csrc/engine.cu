@@ -388,7 +388,7 @@ struct mmae_engine {
   int gemm(bool ta, bool tb, int64_t m, int64_t n, int64_t k, const float* A, int64_t lda, const float* B,
            int64_t ldb, float* Cp, int64_t ldc, const NoiseView& nv, const Epilogue& ep, int64_t* n_partials,
            bool allow_splitk) {
-    GemmArgs g; g.M = m; g.N = n; g.K = k; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = Cp; g.ldc = ldc;
+    GemmArgs g; g.splits = 1; g.k_per_split = 0; g.M = m; g.N = n; g.K = k; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = Cp; g.ldc = ldc;
     g.noise = nv; g.ep = ep;
     last_gemm_tc = false;
     if (cfg.precision == MMAE_PREC_TF32 && tc_gemm_eligible(ta, tb, g)) {
@@ -413,9 +413,23 @@ struct mmae_engine {
       return 0;
     }
     g.ep.colsum_partials = nullptr;
+    g.splits = 1; g.k_per_split = 0;
+    if (allow_splitk && ep.mode == EPI_PLAIN) {
+      const int s = simt_pick_splits(m, n, k, num_sms);
+      if (s > 1) {
+        RET(ensure_splitk((int64_t)s * m * n));
+        g.splits = s; g.k_per_split = (((k + s - 1) / s + SG_BK - 1) / SG_BK) * SG_BK;
+        g.splits = (int)((k + g.k_per_split - 1) / g.k_per_split);
+        g.C = splitk_ws; g.ldc = n; g.ep.beta = 0.f;
+      }
+    }
     cudaError_t e = launch_gemm_simt(ta, tb, g, stream);
     ++launches;
     if (e != cudaSuccess) return cuda_fail(e, "simt gemm launch");
+    if (g.splits > 1) {
+      splitk_reduce_kernel<<<grid_for(m * n, 256), 256, 0, stream>>>(splitk_ws, m * n, g.splits, Cp, n, ldc, ep.beta);
+      CKL("splitk_reduce");
+    }
     if (n_partials) *n_partials = gemm_simt_num_ctas(m, n);
     return 0;
   }
@@ -1234,6 +1248,7 @@ int mmae_debug_gemm(int precision, int transA, int transB, int64_t M, int64_t N,
                     void* stream) {
   GemmArgs g; memset(&g, 0, sizeof(g));
   g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  g.splits = 1; g.k_per_split = 0;
   g.ep.mode = bias || activation ? EPI_BIAS_ACT : EPI_PLAIN; g.ep.bias = bias; g.ep.act = activation; g.ep.beta = beta; g.ep.keep = 1.f;
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == MMAE_PREC_TF32) {

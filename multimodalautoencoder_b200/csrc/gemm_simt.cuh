@@ -22,6 +22,8 @@ struct GemmArgs {
   float* C; int64_t ldc;
   NoiseView noise;      // applied to A's stored (row, col) = (batch row, feature) when enabled
   Epilogue ep;
+  int splits;           // split-K over blockIdx.z (EPI_PLAIN only): slice z of C lives at C + z*M*N with ldc = N
+  int64_t k_per_split;
 };
 
 template <bool TA, bool TB>
@@ -41,7 +43,10 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const GemmArgs g)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int64_t k0 = 0; k0 < g.K; k0 += SG_BK) {
+  const int64_t kbeg = g.splits > 1 ? (int64_t)blockIdx.z * g.k_per_split : 0;
+  const int64_t kend = g.splits > 1 ? min(g.K, kbeg + g.k_per_split) : g.K;
+  float* Cout = g.splits > 1 ? g.C + (int64_t)blockIdx.z * g.M * g.N : g.C;
+  for (int64_t k0 = kbeg; k0 < kend; k0 += SG_BK) {
     // ---- A tile -> As[k][m]
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -50,7 +55,7 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const GemmArgs g)
       else     { m = tid & 63; k = (tid >> 6) + 4 * i; }      // M contiguous in memory
       int64_t gm = m0 + m, gk = k0 + k;
       float v = 0.f;
-      if (gm < g.M && gk < g.K) {
+      if (gm < g.M && gk < kend) {
         if (!TA) { v = __ldg(g.A + gm * g.lda + gk); v = noisy_value(g.noise, gm, (int)gk, v); }
         else     { v = __ldg(g.A + gk * g.lda + gm); v = noisy_value(g.noise, gk, (int)gm, v); }
       }
@@ -64,7 +69,7 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const GemmArgs g)
       else     { k = tid & 15; n = (tid >> 4) + 16 * i; }     // K contiguous
       int64_t gn = n0 + n, gk = k0 + k;
       float v = 0.f;
-      if (gn < g.N && gk < g.K) v = !TB ? __ldg(g.B + gk * g.ldb + gn) : __ldg(g.B + gn * g.ldb + gk);
+      if (gn < g.N && gk < kend) v = !TB ? __ldg(g.B + gk * g.ldb + gn) : __ldg(g.B + gn * g.ldb + gk);
       Bs[k][n] = v;
     }
     __syncthreads();
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const GemmArgs g)
     for (int j = 0; j < 4; ++j) {
       int64_t c = n0 + tx * 4 + j;
       if (c >= g.N) continue;
-      float* p = g.C + r * g.ldc + c;
+      float* p = Cout + r * g.ldc + c;
       float old = (g.ep.beta != 0.f) ? *p : 0.f;
       float aux = auxp ? __ldg(auxp + r * ldaux + c) : 0.f;
       *p = epilogue_apply<false>(g.ep, r, c, acc[i][j], bias_v[j], aux, old, loss_acc);
@@ -120,8 +125,19 @@ inline int64_t gemm_simt_num_ctas(int64_t M, int64_t N) {
   return ((M + SG_BM - 1) / SG_BM) * ((N + SG_BN - 1) / SG_BN);
 }
 
+// Split count for a CUDA-core wgrad whose tile grid would leave most SMs idle (K = batch is the long dimension).
+inline int simt_pick_splits(int64_t M, int64_t N, int64_t K, int num_sms) {
+  const int64_t tiles = gemm_simt_num_ctas(M, N);
+  if (tiles >= num_sms || K < 4096) return 1;
+  int64_t s = (2 * num_sms + tiles - 1) / tiles;
+  const int64_t max_s = K / 1024;
+  if (s > max_s) s = max_s;
+  if (s > 64) s = 64;
+  return (int)(s < 1 ? 1 : s);
+}
+
 inline cudaError_t launch_gemm_simt(bool ta, bool tb, const GemmArgs& g, cudaStream_t st) {
-  dim3 grid((unsigned)((g.M + SG_BM - 1) / SG_BM), (unsigned)((g.N + SG_BN - 1) / SG_BN));
+  dim3 grid((unsigned)((g.M + SG_BM - 1) / SG_BM), (unsigned)((g.N + SG_BN - 1) / SG_BN), (unsigned)(g.splits > 1 ? g.splits : 1));
   if (grid.y > 65535u) return cudaErrorInvalidConfiguration;
   if (!ta && !tb) gemm_simt_kernel<false, false><<<grid, SG_THREADS, 0, st>>>(g);
   else if (!ta && tb) gemm_simt_kernel<false, true><<<grid, SG_THREADS, 0, st>>>(g);

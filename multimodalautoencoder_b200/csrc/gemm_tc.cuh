@@ -115,7 +115,7 @@ inline bool tc_gemm_eligible(bool ta, bool tb, const GemmArgs& g) {
   if (g.noise.enabled) return false;                 // the noisy operand is materialised first on this path
   if ((g.lda & 3) || (g.ldb & 3) || (g.ldc & 3)) return false;
   if (!al(g.A) || !al(g.B) || !al(g.C)) return false;
-  if (g.M < 128 || g.N < 32 || g.K < 32 || (g.N & 3)) return false;
+  if (g.M < 32 || g.N < 32 || g.K < 32 || (g.N & 3)) return false;   // smaller dims ride on TMA zero-fill; below 32 the CUDA-core family wins
   if (g.ep.target && (g.ep.ldt & 3)) return false;
   (void)ta; (void)tb;
   return true;

@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+CMD="python bench.py --workload small --steps 2 --warmup 1 --no-cpu-baseline --no-e2e"
+MMAE_PROFILE_DUMP=1 $CMD > gpurun_out/small_plain.log 2> gpurun_out/small_dump.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/small_launches.csv $CMD > gpurun_out/small_ncu.log 2>&1
+echo rc=$?

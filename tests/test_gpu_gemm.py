@@ -5,7 +5,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(128, 64, 32), (256, 256, 64), (1000, 320, 200), (4096, 2048, 512), (300, 100, 1000), (2048, 4096, 256),
+SHAPES = [(64, 128, 4096), (32, 32, 32), (128, 64, 32), (256, 256, 64), (1000, 320, 200), (4096, 2048, 512), (300, 100, 1000), (2048, 4096, 256),
           (136, 36, 40), (640, 200, 100)]
 
 
@@ -27,7 +27,7 @@ def test_simt_gemm(shape, ta, tb):
     C = debug_gemm(A, B, ta, tb, precision='fp32')
     torch.cuda.synchronize()
     err = (C.double() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
-    assert err < 2e-6, err
+    assert err < 5e-6, err      # fp32 FMA accumulation over K up to 4096
 
 
 @pytest.mark.parametrize('ta', [False, True])

@@ -350,3 +350,22 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError):
         e.train_step(np.zeros((4, 320), np.float32), noise=True)                         # no descriptor yet
     e.close()
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'tf32'])
+def test_large_batch_wgrad_splitk(prec):
+    """B = 8192: the weight-gradient GEMMs contract over the batch and split K across CTAs in both families
+    (fixed-order slice reduction); also exercises decoder wgrads with fewer than 128 output rows."""
+    ocfg, ecfg = make_cfgs(precision=prec, tie=False, lam=0.0)
+    B = 8192
+    rng, X = _data(ocfg, B, 12)
+    P = O.init_params(ocfg, rng)
+    e = _engine(ecfg, P)
+    c, G = O.train_step(ocfg, {k: v.copy() for k, v in P.items()}, O.AdamState(), X, X)
+    e.train_step(X.astype(np.float32), noise=False)
+    tol = TOL[prec]
+    assert abs(e.scalars()['recon_loss'] - c['recon_loss']) <= tol['loss'] * c['recon_loss']
+    for k, g in G.items():
+        ok, info = _grad_ok(e.get_gradient(k), g, tol)
+        assert ok, (k, info)
+    e.close()
