@@ -127,8 +127,12 @@ struct mmae_engine {
   float* ds_X[2] = {nullptr, nullptr}; float* ds_Y[2] = {nullptr, nullptr};
   int64_t ds_rows[2] = {0, 0}; int ds_ycols[2] = {0, 0};
 
-  // ---- NCCL
+  // ---- NCCL: gradient buckets are all-reduced on comm_stream while backward keeps running on `stream`
   void* comm = nullptr; int world = 1, rank = 0;
+  cudaStream_t comm_stream = nullptr;
+  std::vector<cudaEvent_t> comm_events; size_t comm_ev_used = 0;
+  cudaEvent_t comm_done = nullptr;
+  int64_t buckets_issued = 0;
 
   int64_t launches = 0;
 
@@ -232,6 +236,8 @@ struct mmae_engine {
     CK(cudaGetDevice(&device));
     CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&comm_done, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&xin_free[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&xin_ready[i], cudaEventDisableTiming));
@@ -358,7 +364,10 @@ struct mmae_engine {
     for (int i = 0; i < 2; ++i) { if (xin_free[i]) cudaEventDestroy(xin_free[i]); if (xin_ready[i]) cudaEventDestroy(xin_ready[i]); }
     for (auto& r : prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (copy_stream) cudaStreamDestroy(copy_stream);
-    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    if (comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(comm); comm = nullptr; }
+    for (auto ev : comm_events) cudaEventDestroy(ev);
+    if (comm_done) cudaEventDestroy(comm_done);
+    if (comm_stream) cudaStreamDestroy(comm_stream);
   }
 
   // K-major shadow of a weight variable (refreshed lazily after set_variable / Adam); null if w is not a variable
@@ -590,6 +599,7 @@ struct mmae_engine {
       RET(bias_grad(d, B, dout, dout, gvar(bn), d_fused));
       Epilogue ew = epi(EPI_PLAIN); ew.beta = (cfg.tie_weights && !cls_pass) ? 1.f : 0.f;   // tied: decoder part already there
       RET(gemm(true, false, din, dout, B, a_in, din, d, dout, gvar(wn), dout, nv, ew, nullptr, true));
+      RET(bucket_vars(wn, bn));
       if (i == 0) break;
       const bool var_here = cfg.variational && i == L - 1;
       Epilogue ed = epi(var_here ? EPI_PLAIN : EPI_DGRAD);
@@ -600,6 +610,7 @@ struct mmae_engine {
         RET(colsum(glv, B, E, E, gvar("variance_bias")));
         Epilogue ev = epi(EPI_PLAIN);
         RET(gemm(true, false, din, E, B, a_in, din, glv, E, gvar("variance_weights"), E, noise_view(false), ev, nullptr, true));
+        RET(bucket_vars("variance_weights", "variance_bias"));
         Epilogue e2 = epi(EPI_DGRAD); e2.beta = 1.f; e2.saved = ea[i - 1]; e2.lds = din; e2.act = cfg.activation;
         if (keep < 1.f) set_dropout(e2, keep, (uint32_t)(i - 1), din);
         e2.colsum_partials = colpart;
@@ -637,6 +648,7 @@ struct mmae_engine {
       RET(gemm(false, !cfg.tie_weights, B, din, dout, d, ldd, pvar(wn), cfg.tie_weights ? din : dout, nxt, din,
                noise_view(false), ed, nullptr, false));
       d_fused = last_gemm_tc;
+      if (cfg.tie_weights) RET(bucket_vars(bn, bn)); else RET(bucket_vars(wn, bn));   // this decoder layer's gradients are final
       d = nxt; ldd = din; nxt = (nxt == dA) ? dB : dA;
     }
     if (cfg.variational) {
@@ -666,6 +678,7 @@ struct mmae_engine {
       RET(bias_grad(d, B, dout, ldd, gvar(bn), d_fused));
       Epilogue ew = epi(EPI_PLAIN);
       RET(gemm(true, false, din, dout, B, u_in, din, d, ldd, gvar(wn), dout, noise_view(false), ew, nullptr, true));
+      RET(bucket_vars(wn, bn));
       const bool act_prev = i > 0 && (i - 1) < L - 1;
       Epilogue ed = epi(act_prev ? EPI_DGRAD : EPI_PLAIN);
       if (act_prev) { ed.saved = ha[i - 1]; ed.lds = din; ed.act = cfg.head_activation; if (keep < 1.f) set_dropout(ed, keep, 64u + (uint32_t)(i - 1), din); }
@@ -689,14 +702,45 @@ struct mmae_engine {
   int unpack_sums() {
     pack_sums_kernel<<<1, 32, 0, stream>>>(d_sums, G + nP, 0); CKL("unpack_sums"); return 0;
   }
-  int allreduce_grads() {
-    if (!comm || world <= 1) return 0;
-    RET(pack_sums());
-    int r = g_nccl.AllReduce(G, G, (size_t)(nP + 8), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, stream);
+  bool dp_on() const { return comm != nullptr && world > 1; }
+
+  // All-reduce G[begin, end) on the communication stream once everything enqueued so far on `stream` is done.
+  int bucket_allreduce(int64_t begin, int64_t end) {
+    if (!dp_on() || end <= begin) return 0;
+    if (comm_ev_used == comm_events.size()) {
+      cudaEvent_t ev; CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); comm_events.push_back(ev);
+    }
+    cudaEvent_t ev = comm_events[comm_ev_used++];
+    CK(cudaEventRecord(ev, stream));
+    CK(cudaStreamWaitEvent(comm_stream, ev, 0));
+    int r = g_nccl.AllReduce(G + begin, G + begin, (size_t)(end - begin), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, comm_stream);
     if (r != 0) return fail(MMAE_ERR_COMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    ++buckets_issued;
+    return 0;
+  }
+  // bucket = the gradient range of the named variables (adjacent in the flat layout)
+  int bucket_vars(const char* first, const char* last) {
+    if (!dp_on()) return 0;
+    Var* a = find(first); Var* b = find(last);
+    if (!a || !b) return 0;
+    return bucket_allreduce(a->off, b->off + align4(b->count()));
+  }
+  // loss partial sums travel as the 8-float tail of G
+  int sums_allreduce() {
+    if (!dp_on()) return 0;
+    RET(pack_sums());
+    return bucket_allreduce(nP, nP + 8);
+  }
+  // the update (and the scalars) must see fully reduced gradients
+  int join_comm() {
+    if (!dp_on()) return 0;
+    CK(cudaEventRecord(comm_done, comm_stream));
+    CK(cudaStreamWaitEvent(stream, comm_done, 0));
+    comm_ev_used = 0;
     RET(unpack_sums());
     return 0;
   }
+  int allreduce_grads() { return join_comm(); }
   int finalize_scalars(int64_t B, bool recon, bool headl) {
     FinalizeArgs a; a.sums = d_sums; a.scalars = d_scalars; a.loss = cfg.loss_func; a.variational = cfg.variational;
     a.n_elems = (double)gbatch(B) * F; a.batch = (double)gbatch(B);
@@ -763,6 +807,7 @@ int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float kee
   mmae_engine::FwdOpts o; o.X = X; o.target = target ? target : X; o.labels = nullptr; o.B = B; o.noise = use_noise != 0; o.keep = keep;
   o.train_recon = true; o.decoder = true; o.headp = false; o.recon_out = nullptr;
   r = e->forward(o); if (r) return r;
+  r = e->sums_allreduce(); if (r) return r;          // overlaps the whole backward pass
   r = e->backward_recon(B, keep); if (r) return r;
   e->last_B = B;
   e->rng_step += 1;
@@ -776,6 +821,7 @@ int do_cls(mmae_engine* e, const float* X, const float* Y, int64_t B, int use_no
   o.train_recon = false; o.decoder = false; o.headp = true; o.recon_out = nullptr;
   r = e->forward(o); if (r) return r;
   r = e->head_loss(Y, B, true, nullptr, nullptr); if (r) return r;
+  r = e->sums_allreduce(); if (r) return r;
   r = e->backward_cls(B, keep); if (r) return r;
   e->last_B = B;
   e->rng_step += 1;
