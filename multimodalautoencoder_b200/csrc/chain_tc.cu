@@ -1,0 +1,406 @@
+// Device side of the whole-network chain kernel (design notes in chain_tc.cuh).
+#include "chain_tc.cuh"
+#include "gemm_tc_kernel.cuh"
+
+namespace mmae {
+
+// ------------------------------------------------------------------ PTX wrappers specific to the chain
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return r;
+}
+__host__ __device__ inline uint32_t idesc_tf32_rt(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One epilogue warp's staging: two [32 rows][32 cols] fp32 tiles in the TMA 128B-swizzle layout.  Thread = row:
+// 16-byte chunk q of row r lives at r*128 + ((q ^ (r & 7)) << 4)  (conflict-free for the 8 lanes of a quarter warp).
+struct EpiStage {
+  uint8_t* buf[2];
+  uint64_t* aux_bar[2];
+  uint32_t aux_phase[2];
+  uint32_t uses;          // tiles handed to TMA so far (alternates the two buffers)
+};
+__device__ __forceinline__ float4* row_chunk(uint8_t* tile, int lane, int q) {
+  return reinterpret_cast<float4*>(tile + lane * 128 + ((q ^ (lane & 7)) << 4));
+}
+
+// ------------------------------------------------------------------ epilogue of a non-final op, one 32-column chunk
+// v = drop(act(acc + bias)); TMEM <- tf32(v) in place; optional global copy through a swizzled tile + TMA store.
+template <int ACT, bool DROP>
+__device__ __forceinline__ void chain_act_chunk(const ChainOp& o, const CUtensorMap* tmO, uint32_t taddr, int col0, int64_t tile_row0,
+                                                int quad, int lane, const float* bias_s, EpiStage& es) {
+  uint32_t r[32];
+  tc_ld32(taddr, r);
+  uint8_t* tile = es.buf[es.uses & 1];
+  if (o.has_out) {                       // the store issued two tiles ago has finished reading this buffer
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+  }
+  const int64_t grow = tile_row0 + quad * 32 + lane + o.ep.row0;      // this thread's global row (dropout stream)
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(bias_s + col0 + q * 4);     // warp-uniform address: broadcast
+    float v[4] = {__uint_as_float(r[q * 4 + 0]) + b.x, __uint_as_float(r[q * 4 + 1]) + b.y,
+                  __uint_as_float(r[q * 4 + 2]) + b.z, __uint_as_float(r[q * 4 + 3]) + b.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[e] = act_fast_t<ACT>(v[e]);
+      if (DROP) {
+        uint32_t w = philox_word((uint64_t)grow * (uint64_t)o.ep.drop_width + (uint64_t)(col0 + q * 4 + e), o.ep.drop_stream, o.ep.step, o.ep.seed);
+        v[e] = ((w >> 8) < o.ep.keep_thr) ? v[e] / o.ep.keep : 0.f;
+      }
+      r[q * 4 + e] = to_tf32(v[e]);
+    }
+    if (o.has_out) *row_chunk(tile, lane, q) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  tc_st32(taddr, r);
+  if (o.has_out) {
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) { tma_store_2d(tmO, tile, col0, (int)(tile_row0 + quad * 32)); bulk_commit(); }
+    es.uses++;
+  }
+}
+
+template <bool DROP>
+__device__ __forceinline__ void chain_act_dispatch(const ChainOp& o, const CUtensorMap* tmO, uint32_t taddr, int col0, int64_t tile_row0,
+                                                   int quad, int lane, const float* bias_s, EpiStage& es) {
+  switch (o.ep.act) {
+    case MMAE_ACT_RELU: chain_act_chunk<MMAE_ACT_RELU, DROP>(o, tmO, taddr, col0, tile_row0, quad, lane, bias_s, es); break;
+    case MMAE_ACT_TANH: chain_act_chunk<MMAE_ACT_TANH, DROP>(o, tmO, taddr, col0, tile_row0, quad, lane, bias_s, es); break;
+    case MMAE_ACT_SOFTSIGN: chain_act_chunk<MMAE_ACT_SOFTSIGN, DROP>(o, tmO, taddr, col0, tile_row0, quad, lane, bias_s, es); break;
+    case MMAE_ACT_SOFTPLUS: chain_act_chunk<MMAE_ACT_SOFTPLUS, DROP>(o, tmO, taddr, col0, tile_row0, quad, lane, bias_s, es); break;
+    default: chain_act_chunk<MMAE_ACT_LINEAR, DROP>(o, tmO, taddr, col0, tile_row0, quad, lane, bias_s, es); break;
+  }
+}
+
+// ------------------------------------------------------------------ epilogue of the final op, one 32-column chunk
+// l = acc + bias; loss += f(l, target); out = dLoss/dl (TRAIN) or decoded_X (PRED).  The target tile was loaded by
+// TMA into `tile`; the result overwrites it in place and leaves with a TMA store.
+template <int MODE, int LOSS>
+__device__ __forceinline__ void chain_final_chunk(const ChainOp& o, uint32_t taddr, int col0, bool row_valid, int lane, const float* bias_s,
+                                                  uint8_t* tile, bool has_aux, float& loss_acc) {
+  uint32_t r[32];
+  tc_ld32(taddr, r);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4* cp = row_chunk(tile, lane, q);
+    const float4 b = *reinterpret_cast<const float4*>(bias_s + col0 + q * 4);
+    float4 x4 = has_aux ? *cp : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+    const float bs[4] = {b.x, b.y, b.z, b.w};
+    float outv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float l = __uint_as_float(r[q * 4 + e]) + bs[e], x = xs[e];
+      const bool cnt = has_aux && row_valid && (col0 + q * 4 + e < o.N);
+      float lossv;
+      if (LOSS == MMAE_LOSS_SIGMOID_CE) {
+        const float ex = __expf(-fabsf(l));
+        const float inv = __fdividef(1.f, 1.f + ex);
+        const float s = l >= 0.f ? inv : ex * inv;
+        lossv = fmaxf(l, 0.f) - l * x + __logf(1.f + ex);
+        outv[e] = (MODE == EPI_LOSS_TRAIN) ? (s - x) : s;
+      } else if (LOSS == MMAE_LOSS_RMSE) {
+        const float d = l - x;
+        lossv = d * d;
+        outv[e] = (MODE == EPI_LOSS_TRAIN) ? d : l;
+      } else {
+        lossv = -x * __logf(l);
+        outv[e] = (MODE == EPI_LOSS_TRAIN) ? __fdividef(-x, l) : l;
+      }
+      if (cnt) loss_acc += lossv;
+    }
+    *cp = make_float4(outv[0], outv[1], outv[2], outv[3]);
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void chain_final_dispatch(const ChainOp& o, uint32_t taddr, int col0, bool row_valid, int lane, const float* bias_s,
+                                                     uint8_t* tile, bool has_aux, float& loss_acc) {
+  switch (o.ep.loss) {
+    case MMAE_LOSS_SIGMOID_CE: chain_final_chunk<MODE, MMAE_LOSS_SIGMOID_CE>(o, taddr, col0, row_valid, lane, bias_s, tile, has_aux, loss_acc); break;
+    case MMAE_LOSS_RMSE: chain_final_chunk<MODE, MMAE_LOSS_RMSE>(o, taddr, col0, row_valid, lane, bias_s, tile, has_aux, loss_acc); break;
+    default: chain_final_chunk<MODE, MMAE_LOSS_CE>(o, taddr, col0, row_valid, lane, bias_s, tile, has_aux, loss_acc); break;
+  }
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* xring = smem;
+  uint8_t* wring = xring + CH_XSTAGES * CH_XBYTES;
+  uint8_t* epi_tiles = wring + CH_WRING_BYTES;
+  float* bias_s = reinterpret_cast<float*>(epi_tiles + CH_EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + CH_BIAS_FLOATS * 4);
+  uint64_t* xfull = bars;                               // [CH_XSTAGES]
+  uint64_t* xempty = xfull + CH_XSTAGES;                // [CH_XSTAGES]
+  uint64_t* wfull = xempty + CH_XSTAGES;                // [CH_MAX_WSTAGES]
+  uint64_t* wempty = wfull + CH_MAX_WSTAGES;            // [CH_MAX_WSTAGES]
+  uint64_t* mma_done = wempty + CH_MAX_WSTAGES;         // [CH_MAX_OPS]      accumulator of op i complete
+  uint64_t* chunk_done = mma_done + CH_MAX_OPS;         // [CH_MAX_OPS][CH_MAX_CHUNKS]  32 activated columns back in TMEM
+  uint64_t* last_done = chunk_done + CH_MAX_OPS * CH_MAX_CHUNKS;   // [1]    final op's accumulator drained
+  uint64_t* aux_bar = last_done + 1;                    // [CH_EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + CH_EPI_WARPS * 2);
+  float* epi_red = reinterpret_cast<float*>(tmem_slot + 2);       // [CH_EPI_WARPS]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int last = p.nops - 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
+    for (int i = 0; i < p.nops; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB[i]) : "memory");
+  }
+  if (warp == 2 && lane == 0) {
+    for (int s = 0; s < CH_XSTAGES; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
+    for (int s = 0; s < CH_MAX_WSTAGES; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+    for (int i = 0; i < CH_MAX_OPS; ++i) mbar_init(&mma_done[i], 1);
+    for (int i = 0; i < CH_MAX_OPS * CH_MAX_CHUNKS; ++i) mbar_init(&chunk_done[i], 4);     // one warp per lane quadrant
+    mbar_init(last_done, CH_EPI_WARPS);
+    for (int i = 0; i < CH_EPI_WARPS * 2; ++i) mbar_init(&aux_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 3) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(CH_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // zero-padded bias table: bias_s[op.bias_off + col]
+  for (int i = 0; i < p.nops; ++i) {
+    const ChainOp& o = p.op[i];
+    const int w = o.n_chunk * o.n_chunks;
+    for (int c = threadIdx.x; c < w; c += CH_THREADS)
+      bias_s[o.bias_off + c] = (o.ep.bias && c < o.N) ? __ldg(o.ep.bias + c) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== X producer: rows of this CTA's tiles, k-chunk by k-chunk =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const int K0 = p.op[0].K;
+      for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x) {
+        for (int k = 0; k < K0; k += TC_BK) {
+          mbar_wait(&xempty[stage], phase ^ 1);
+          mbar_expect_tx(&xfull[stage], CH_XBYTES);
+          tma_load_2d(&p.tmA, &xfull[stage], xring + stage * CH_XBYTES, k, t * TC_BM);
+          if (++stage == CH_XSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== W producer: every op's weight k-chunks, once per tile (L2-resident) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x) {
+        for (int i = 0; i < p.nops; ++i) {
+          const ChainOp& o = p.op[i];
+          const uint32_t bytes = (uint32_t)o.n_chunk * TC_BK * 4;
+          for (int nc = 0; nc < o.n_chunks; ++nc) {
+            for (int k = 0; k < o.K; k += TC_BK) {
+              mbar_wait(&wempty[stage], phase ^ 1);
+              mbar_expect_tx(&wfull[stage], bytes);
+              tma_load_2d(&p.tmB[i], &wfull[stage], wring + stage * p.w_slot_bytes, k, nc * o.n_chunk);
+              if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer =====================
+    int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x, ++it) {
+      const uint32_t par = it & 1;
+      for (int i = 0; i < p.nops; ++i) {
+        const ChainOp& o = p.op[i];
+        if (i == last && it > 0) { mbar_wait(last_done, par ^ 1); tc_fence_after(); }   // previous tile's result drained
+        const uint32_t idesc = idesc_tf32_rt(TC_BM, o.n_chunk);
+        for (int nc = 0; nc < o.n_chunks; ++nc) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)(o.d_col + nc * o.n_chunk);
+          uint32_t accumulate = 0;
+          for (int k = 0; k < o.K; k += TC_BK) {
+            if (o.a_tmem && nc == 0) mbar_wait(&chunk_done[(i - 1) * CH_MAX_CHUNKS + (k >> 5)], par);   // A columns [k, k+32) written
+            mbar_wait(&wfull[ws], wph);
+            if (!o.a_tmem) mbar_wait(&xfull[xs], xph);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t sb = smem_u32(wring + ws * p.w_slot_bytes);
+              const int ksteps = min(TC_BK / TC_UMMA_K, (o.K - k + TC_UMMA_K - 1) / TC_UMMA_K);
+              if (o.a_tmem) {
+                const uint32_t ta = tmem_base + (uint32_t)(o.a_col + k);
+                for (int kk = 0; kk < ksteps; ++kk) {
+                  tc_mma_tf32_ts(tmem_d, ta + kk * TC_UMMA_K, make_smem_desc(sb + kk * 32, 16, 1024), idesc, accumulate);
+                  accumulate = 1;
+                }
+              } else {
+                const uint32_t sa = smem_u32(xring + xs * CH_XBYTES);
+                for (int kk = 0; kk < ksteps; ++kk) {
+                  tc_mma_tf32(tmem_d, make_smem_desc(sa + kk * 32, 16, 1024), make_smem_desc(sb + kk * 32, 16, 1024), idesc, accumulate);
+                  accumulate = 1;
+                }
+                tc_commit(&xempty[xs]);
+              }
+              tc_commit(&wempty[ws]);
+            }
+            __syncwarp();
+            if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
+            if (!o.a_tmem) { if (++xs == CH_XSTAGES) { xs = 0; xph ^= 1; } }
+          }
+        }
+        if (lane == 0) tc_commit(&mma_done[i]);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= CH_EPI_WARP0) {
+    // ===================== epilogue warps: quadrant = warp % 4, two warps per quadrant =====================
+    const int ew = warp - CH_EPI_WARP0;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    EpiStage es;
+    es.buf[0] = epi_tiles + ew * 2 * CH_EPI_TILE; es.buf[1] = es.buf[0] + CH_EPI_TILE;
+    es.aux_bar[0] = &aux_bar[ew * 2]; es.aux_bar[1] = &aux_bar[ew * 2 + 1];
+    es.aux_phase[0] = es.aux_phase[1] = 0; es.uses = 0;
+    float loss_acc = 0.f;
+    const ChainOp& lo = p.op[last];
+    const bool has_aux = lo.ep.target != nullptr;
+    const int lchunks = lo.n_chunks * lo.n_chunk / 32;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x, ++it) {
+      const uint32_t par = it & 1;
+      const int64_t tile_row0 = (int64_t)t * TC_BM;
+      const int row0 = (int)(tile_row0 + quad * 32);
+      // ---- non-final ops: activated values back into TMEM (+ optional global copy)
+      for (int i = 0; i < last; ++i) {
+        const ChainOp& o = p.op[i];
+        mbar_wait(&mma_done[i], par);
+        tc_fence_after();
+        const int chunks = o.n_chunk / 32;
+        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)o.d_col;
+        for (int ch = half; ch < chunks; ch += 2) {
+          if (o.ep.keep < 1.f) chain_act_dispatch<true>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, quad, lane, bias_s + o.bias_off, es);
+          else chain_act_dispatch<false>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, quad, lane, bias_s + o.bias_off, es);
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&chunk_done[i * CH_MAX_CHUNKS + ch]);
+        }
+      }
+      // ---- final op: the target tile of my first chunk travels while the last MMAs run
+      {
+        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)lo.d_col;
+        if (has_aux && half < lchunks && half * 32 < lo.N) {
+          const int b = es.uses & 1;
+          if (lane == 0) {
+            bulk_wait_read<1>();          // the store that last used this buffer is done reading it
+            mbar_expect_tx(es.aux_bar[b], CH_EPI_TILE);
+            tma_load_2d(&p.tmT, es.aux_bar[b], es.buf[b], half * 32, row0);
+          }
+          __syncwarp();
+        }
+        mbar_wait(&mma_done[last], par);
+        tc_fence_after();
+        const bool row_valid = (int64_t)row0 + lane < p.M;
+        for (int ch = half; ch < lchunks; ch += 2) {
+          if (ch * 32 >= lo.N) break;                                   // padding columns only
+          const int b = es.uses & 1;
+          const int nxt = ch + 2;
+          if (has_aux && nxt < lchunks && nxt * 32 < lo.N) {            // prefetch the next chunk's target tile
+            if (lane == 0) {
+              bulk_wait_read<0>();
+              mbar_expect_tx(es.aux_bar[b ^ 1], CH_EPI_TILE);
+              tma_load_2d(&p.tmT, es.aux_bar[b ^ 1], es.buf[b ^ 1], nxt * 32, row0);
+            }
+            __syncwarp();
+          } else if (!has_aux) {
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+          }
+          if (has_aux) { mbar_wait(es.aux_bar[b], es.aux_phase[b]); es.aux_phase[b] ^= 1; }
+          uint8_t* tile = es.buf[b];
+          if (lo.ep.mode == EPI_LOSS_TRAIN) chain_final_dispatch<EPI_LOSS_TRAIN>(lo, tbase + ch * 32, ch * 32, row_valid, lane, bias_s + lo.bias_off, tile, has_aux, loss_acc);
+          else chain_final_dispatch<EPI_LOSS_PRED>(lo, tbase + ch * 32, ch * 32, row_valid, lane, bias_s + lo.bias_off, tile, has_aux, loss_acc);
+          __syncwarp();
+          if (lo.ep.colsum_partials && row0 < p.M) {
+            // bias gradient: column sums of this warp's 32 rows, read back column-wise from the swizzled tile
+            const int col = ch * 32 + lane;
+            const int nrows = (int)min((int64_t)32, p.M - row0);
+            float cs = 0.f;
+            for (int r = 0; r < nrows; ++r)
+              cs += *reinterpret_cast<const float*>(tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+            if (col < lo.N) lo.ep.colsum_partials[(int64_t)(row0 >> 5) * lo.N + col] = cs;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&p.tmO[last], tile, ch * 32, row0); bulk_commit(); }
+          es.uses++;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(last_done);
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every output tile has landed
+    if (lo.ep.loss_partials) {
+      float w = warp_sum(loss_acc);
+      if (lane == 0) epi_red[ew] = w;
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps only
+      if (ew == 0 && lane == 0) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < CH_EPI_WARPS; ++i) sacc += epi_red[i];
+        lo.ep.loss_partials[blockIdx.x] = sacc;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CH_TMEM_COLS) : "memory");
+  }
+}
+
+cudaError_t chain_launch(const ChainParams& p, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  chain_tc_kernel<<<grid, CH_THREADS, CH_SMEM, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace mmae

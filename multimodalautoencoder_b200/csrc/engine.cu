@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "chain_tc.cuh"
 #include "kernels.cuh"
 
 using namespace mmae;
@@ -314,6 +315,10 @@ struct mmae_engine {
     return 0;
   }
 
+  // Workspaces grow on demand in three groups so that a 10 M-row fill-in pass does not allocate training buffers:
+  //   base  (ensure_cap)  : noise descriptor, embedding, reconstruction, head outputs, reduction scratch
+  //   acts  (ensure_acts) : materialised noisy X, saved activations, delta ping-pong, bias-gradient partials
+  //   host  (ensure_host) : double-buffered staging of host-fed batches
   int ensure_cap(int64_t B) {
     if (B <= cap) return 0;
     CK(cudaStreamSynchronize(stream));
@@ -321,14 +326,9 @@ struct mmae_engine {
     const int zw = (F + 31) / 32;
     RET(realloc_dev(zero_bits, nc * zw)); RET(realloc_dev(mod_bits, nc)); RET(realloc_dev(miss_bits, nc));
     noise_rows = 0;
-    for (int i = 0; i < 2; ++i) { RET(realloc_dev(xin[i], nc * F)); RET(realloc_dev(yin[i], nc * std::max(C, 1))); }
-    RET(realloc_dev(noisy, nc * F));
-    for (int i = 0; i + 1 < L; ++i) RET(realloc_dev(ea[i], nc * layers[i]));
-    for (int j = 0; j + 1 < L; ++j) RET(realloc_dev(da[j], nc * layers[L - 2 - j]));
     RET(realloc_dev(mu, nc * E));
     if (cfg.variational) { RET(realloc_dev(lv, nc * E)); RET(realloc_dev(eps, nc * E)); RET(realloc_dev(emb, nc * E)); RET(realloc_dev(glv, nc * E)); }
     RET(realloc_dev(out, nc * F));
-    RET(realloc_dev(dA, nc * maxw)); RET(realloc_dev(dB, nc * maxw));
     if (H > 0) {
       for (int i = 0; i < H; ++i) RET(realloc_dev(ha[i], nc * head[i]));
       RET(realloc_dev(hlogits, nc * C)); RET(realloc_dev(hdelta, nc * C));
@@ -340,9 +340,31 @@ struct mmae_engine {
     if (pc > partials_cap) { RET(realloc_dev(partials, pc)); partials_cap = pc; }
     int64_t cs = (int64_t)64 * std::max(F, maxw);
     if (cs > colsum_cap) { RET(realloc_dev(colsum_ws, cs)); colsum_cap = cs; }
+    cap = nc;
+    return 0;
+  }
+  int64_t cap_acts = 0, cap_host = 0;
+  int ensure_acts(int64_t B) {
+    RET(ensure_cap(B));
+    if (B <= cap_acts) return 0;
+    CK(cudaStreamSynchronize(stream));
+    int64_t nc = std::max<int64_t>(B, cap_acts + cap_acts / 2);
+    RET(realloc_dev(noisy, nc * F));
+    for (int i = 0; i + 1 < L; ++i) RET(realloc_dev(ea[i], nc * layers[i]));
+    for (int j = 0; j + 1 < L; ++j) RET(realloc_dev(da[j], nc * layers[L - 2 - j]));
+    RET(realloc_dev(dA, nc * maxw)); RET(realloc_dev(dB, nc * maxw));
     int64_t cpn = ((nc + 31) / 32) * (int64_t)std::max(F, maxw);
     if (cpn > colpart_cap) { RET(realloc_dev(colpart, cpn)); colpart_cap = cpn; }
-    cap = nc;
+    cap_acts = nc;
+    return 0;
+  }
+  int ensure_host(int64_t B) {
+    RET(ensure_cap(B));
+    if (B <= cap_host) return 0;
+    CK(cudaStreamSynchronize(stream)); CK(cudaStreamSynchronize(copy_stream));
+    int64_t nc = std::max<int64_t>(B, cap_host + cap_host / 2);
+    for (int i = 0; i < 2; ++i) { RET(realloc_dev(xin[i], nc * F)); RET(realloc_dev(yin[i], nc * std::max(C, 1))); }
+    cap_host = nc;
     return 0;
   }
 
@@ -482,12 +504,79 @@ struct mmae_engine {
     return 0;
   }
 
+  // Whole-network launch (chain_tc.cuh): encoder + decoder + loss in one persistent tcgen05 kernel, activations
+  // resident in TMEM.  Returns 1 when it ran, 0 when the configuration does not fit (caller runs the per-layer
+  // GEMMs), or a (negative) error code.
+  int64_t chain_launches = 0;
+  int chain_mode = -1;
+  int forward_chain(const FwdOpts& o, const float* a) {
+    if (chain_mode < 0) { const char* ev = getenv("MMAE_CHAIN"); chain_mode = (ev && ev[0] == '0') ? 0 : 1; }
+    if (!chain_mode || cfg.precision != MMAE_PREC_TF32 || cfg.variational || o.B < 32) return 0;
+    const int64_t B = o.B;
+    const bool save = o.train_recon;
+    std::vector<ChainLayer> ls;
+    double flops = 0.0;
+    for (int i = 0; i < L; ++i) {
+      const bool last = i == L - 1;
+      const int din = enc_in(i), dout = layers[i];
+      char wn[32], bn[32]; snprintf(wn, 32, "weights%d", i); snprintf(bn, 32, "encode_biases%d", i);
+      if ((din & 3)) return 0;
+      ChainLayer l; l.K = din; l.N = dout;
+      l.Wkm = shadowT(pvar(wn), din, dout); l.ldw = din;
+      if (!l.Wkm) return 0;
+      l.ep = epi(EPI_BIAS_ACT); l.ep.bias = pvar(bn);
+      if (!last) { l.ep.act = cfg.activation; if (o.keep < 1.f) set_dropout(l.ep, o.keep, (uint32_t)i, dout); l.out = save ? ea[i] : nullptr; }
+      else { l.ep.act = MMAE_ACT_LINEAR; l.out = mu; }
+      l.ldo = dout;
+      ls.push_back(l); flops += 2.0 * din * dout;
+    }
+    float* dst = o.recon_out ? o.recon_out : out;
+    for (int j = 0; j < L; ++j) {
+      const int i = L - 1 - j;
+      const int din = layers[i], dout = enc_in(i);
+      const bool last = j == L - 1;
+      char wn[32], bn[32]; snprintf(bn, 32, "decode_biases%d", i);
+      ChainLayer l; l.K = din; l.N = dout; l.ldw = din;
+      if ((din & 3)) return 0;
+      if (cfg.tie_weights) { snprintf(wn, 32, "weights%d", i); l.Wkm = pvar(wn); }          // W_i [dout, din] is K-major for W_i^T (:284)
+      else { snprintf(wn, 32, "decode_weights%d", i); l.Wkm = shadowT(pvar(wn), din, dout); }
+      if (!l.Wkm) return 0;
+      if (!last) {
+        l.ep = epi(EPI_BIAS_ACT); l.ep.bias = pvar(bn); l.ep.act = cfg.activation;
+        if (o.keep < 1.f) set_dropout(l.ep, o.keep, 32u + (uint32_t)j, dout);
+        l.out = save ? da[j] : nullptr;
+      } else {
+        l.ep = epi(o.train_recon ? EPI_LOSS_TRAIN : EPI_LOSS_PRED); l.ep.bias = pvar(bn); l.ep.loss = cfg.loss_func;
+        l.ep.target = o.target; l.ep.ldt = F; l.ep.loss_partials = o.target ? partials : nullptr;
+        if (o.train_recon) l.ep.colsum_partials = colpart;
+        l.out = dst;
+      }
+      l.ldo = dout;
+      ls.push_back(l); flops += 2.0 * din * dout;
+    }
+    ChainParams cp;
+    if (!chain_build(cp, a, B, F, ls)) return 0;
+    const int grid = std::min(cp.m_tiles, num_sms);
+    int pr = prof_begin(flops * (double)B);
+    if (pr >= 0) { auto& R = prof_recs[pr]; R.m = B; R.n = -1; R.k = -1; R.ta = 0; R.tb = 1; R.splits = 1; }
+    cudaError_t e = chain_launch(cp, grid, stream);
+    prof_end(pr);
+    ++launches; ++chain_launches;
+    if (e != cudaSuccess) return cuda_fail(e, "chain launch");
+    cur_emb = mu;
+    d_fused = o.train_recon;
+    last_gemm_tc = true;
+    if (o.target) { int r = reduce_partials(grid, 0); if (r) return r; }
+    return 1;
+  }
+
   int forward(const FwdOpts& o) {
     const int64_t B = o.B;
     const int act = cfg.activation;
     const float* a = o.X;
     NoiseView nv = noise_view(o.noise);
-    if (o.noise && cfg.precision == MMAE_PREC_TF32 && B >= 128 && (F & 3) == 0) {
+    if (o.noise || o.train_recon || o.labels) RET(ensure_acts(B));
+    if (o.noise && cfg.precision == MMAE_PREC_TF32 && B >= 32 && (F & 3) == 0) {
       // the tcgen05 family reads its operands through TMA: materialise noisy_X once (first GEMM + its wgrad)
       noise_apply_kernel<<<grid_for(B * F, 256), 256, 0, stream>>>(o.X, noisy, B, F, nv);
       CKL("noise_apply");
@@ -495,7 +584,10 @@ struct mmae_engine {
     }
     x_eff = a; x_noise = nv;
     int64_t lda = F;
-    for (int i = 0; i < L; ++i) {
+    bool chained = false;
+    if (o.decoder && !nv.enabled) { int cr = forward_chain(o, a); if (cr < 0) return cr; chained = cr == 1; }
+    if (!chained) RET(ensure_acts(B));
+    for (int i = 0; i < L && !chained; ++i) {
       const bool last = i == L - 1;
       const int din = enc_in(i), dout = layers[i];
       char wn[32], bn[32]; snprintf(wn, 32, "weights%d", i); snprintf(bn, 32, "encode_biases%d", i);
@@ -521,7 +613,7 @@ struct mmae_engine {
       RET(reduce_partials(g, 1));
       cur_emb = emb;
     }
-    if (o.decoder) {
+    if (o.decoder && !chained) {
       const float* u = cur_emb; int64_t ldu = E;
       for (int j = 0; j < L; ++j) {
         const int i = L - 1 - j;
@@ -830,7 +922,7 @@ int do_cls(mmae_engine* e, const float* X, const float* Y, int64_t B, int use_no
 
 // stage a host batch into the double-buffered device input; returns the device pointers
 int stage_host(mmae_engine* e, const float* X_host, const float* Y_host, int64_t B, int ycols, float** Xd, float** Yd) {
-  int r = e->ensure_cap(B); if (r) return r;
+  int r = e->ensure_host(B); if (r) return r;
   const int t = e->xin_turn; e->xin_turn ^= 1;
   cudaError_t ce;
   // the copy may start once the compute that last read this buffer has finished
@@ -1116,7 +1208,8 @@ int mmae_forward_host(mmae_engine* e, const float* X_host, const float* target_h
                       int64_t batch, int use_noise, float keep, uint32_t want, const mmae_outputs* oh) {
   ENTER(e);
   if (!X_host) return e->fail(MMAE_ERR_INVALID, "null X");
-  int r = e->ensure_cap(batch); if (r) return r;
+  int r = e->ensure_host(batch); if (r) return r;
+  r = e->ensure_acts(batch); if (r) return r;      // output staging borrows the delta / noisy workspaces
   const int ycols = e->H ? (e->cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? e->C : 1) : 0;
   float *Xd = nullptr, *Yd = nullptr;
   int t = stage_host(e, X_host, labels_host, batch, ycols, &Xd, &Yd); if (t < 0) return t;
@@ -1180,7 +1273,7 @@ int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, 
   ENTER(e);
   if (slot < 0 || slot > 1 || !e->ds_X[slot]) return e->fail(MMAE_ERR_STATE, "dataset slot is empty");
   if (classification && !e->ds_Y[slot]) return e->fail(MMAE_ERR_STATE, "dataset slot has no labels");
-  int r = e->ensure_cap(batch); if (r) return r;
+  int r = e->ensure_host(batch); if (r) return r;
   cudaError_t ce;
   if (idx_host) {
     ce = cudaMemcpyAsync(e->d_idx, idx_host, (size_t)batch * 8, cudaMemcpyHostToDevice, e->stream);
@@ -1238,6 +1331,7 @@ int mmae_set_shard(mmae_engine* e, int64_t global_batch, int64_t first_row) {
 }
 
 int64_t mmae_kernel_launches(const mmae_engine* e) { return e ? e->launches : 0; }
+int64_t mmae_chain_launches(const mmae_engine* e) { return e ? e->chain_launches : 0; }
 
 int mmae_set_profiling(mmae_engine* e, int on) {
   ENTER(e);

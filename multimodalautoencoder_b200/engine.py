@@ -427,6 +427,11 @@ class Engine:
     def kernel_launches(self):
         return self.lib.mmae_kernel_launches(self._h)
 
+    @property
+    def chain_launches(self):
+        """How many of the launches were the whole-network (encode + decode + loss) kernel."""
+        return self.lib.mmae_chain_launches(self._h)
+
 
 def debug_gemm(A, B, transA=False, transB=False, bias=None, activation='linear', precision='tf32', C_init=None, beta=0.0):
     """C = op(A) op(B) through one of the engine's GEMM families (tests / bench only)."""

@@ -1,0 +1,106 @@
+"""The whole-network tcgen05 kernel (csrc/chain_tc.cu: encoder + decoder + loss in one launch, activations
+resident in TMEM) against (a) the fp64 oracle and (b) the per-layer tcgen05 GEMM path on the same inputs.
+
+Tolerances: the tf32 ones of test_gpu_parity.py (loss <= 1e-3 relative, reconstructions <= 5e-3
+relative-to-max); chain vs per-layer (both round operands to tf32 the same way, only the accumulation order
+inside a tile is shared too) <= 2e-4 relative-to-max on every output.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mmae_oracle as O
+from tests.helpers import make_cfgs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(ecfg, P, chain):
+    from multimodalautoencoder_b200 import Engine
+    old = os.environ.get('MMAE_CHAIN')
+    os.environ['MMAE_CHAIN'] = '1' if chain else '0'
+    try:
+        e = Engine(ecfg)
+        e.set_params({k: v.astype(np.float32) for k, v in P.items()})
+        # the switch is read at the first forward: run one now
+        e.forward(np.zeros((32, ecfg.num_feats), np.float32), recon=True)
+    finally:
+        if old is None:
+            os.environ.pop('MMAE_CHAIN', None)
+        else:
+            os.environ['MMAE_CHAIN'] = old
+    return e
+
+
+CASES = [
+    dict(id='S-untied', kw=dict(tie=False), B=384),
+    dict(id='S-tied-relu-rmse', kw=dict(tie=True, act='relu', loss='mean_squared'), B=1000),
+    dict(id='S-L3-tanh', kw=dict(layers=(128, 64, 32), tie=False, act='tanh'), B=129),
+    dict(id='S-one-layer', kw=dict(layers=(64,), tie=True), B=32),
+    dict(id='S-many-tiles', kw=dict(tie=False), B=128 * 148 * 2 + 77),
+    dict(id='odd-widths', kw=dict(layers=(100, 44), tie=False, act='softplus'), B=257),
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c['id'] for c in CASES])
+def test_chain_forward_matches_oracle_and_layerwise(case):
+    ocfg, ecfg = make_cfgs(precision='tf32', **case['kw'])
+    B = case['B']
+    rng = np.random.default_rng(7)
+    X = rng.uniform(0, 1, (B, ocfg.num_feats)).astype(np.float32)
+    P = O.init_params(ocfg, rng)
+    ec = _engine(ecfg, P, True)
+    el = _engine(ecfg, P, False)
+    n0 = ec.chain_launches
+    rc = ec.forward(X, recon=True, embedding=True, loss=True)
+    assert ec.chain_launches == n0 + 1, 'the whole-network kernel did not run'
+    rl = el.forward(X, recon=True, embedding=True, loss=True)
+    assert el.chain_launches == 0
+    sc, sl = ec.scalars(), el.scalars()
+    c = O.forward(ocfg, P, X.astype(np.float64), X.astype(np.float64))
+    assert abs(sc['recon_loss'] - c['recon_loss']) <= 1e-3 * abs(c['recon_loss'])
+    assert rel_err(rc['recon'].cpu().numpy(), c['decoded']) <= 5e-3
+    assert rel_err(rc['embedding'].cpu().numpy(), c['emb']) <= 5e-3
+    assert abs(sc['recon_loss'] - sl['recon_loss']) <= 1e-5 * abs(sl['recon_loss'])
+    assert rel_err(rc['recon'].cpu().numpy(), rl['recon'].cpu().numpy()) <= 2e-4
+    assert rel_err(rc['embedding'].cpu().numpy(), rl['embedding'].cpu().numpy()) <= 2e-4
+    ec.close(); el.close()
+
+
+@pytest.mark.parametrize('keep', [1.0, 0.5])
+def test_chain_train_step_matches_layerwise(keep):
+    """Training through the chain (saved activations + delta_L + bias-gradient partials written by the fused
+    kernel, per-layer backward) gives the per-layer path's gradients; dropout masks are the same Philox stream."""
+    ocfg, ecfg = make_cfgs(precision='tf32', tie=False, lam=0.001, seed=5)
+    B = 640
+    rng = np.random.default_rng(8)
+    X = rng.uniform(0, 1, (B, 320)).astype(np.float32)
+    P = O.init_params(ocfg, rng)
+    ec = _engine(ecfg, P, True)
+    el = _engine(ecfg, P, False)
+    for e in (ec, el):
+        e.set_rng_step(11)
+        e.gen_noise(B)
+        e.train_step(X, noise=True, keep=keep)
+    assert ec.chain_launches >= 2 and el.chain_launches == 0
+    assert abs(ec.scalars()['recon_loss'] - el.scalars()['recon_loss']) <= 1e-5 * el.scalars()['recon_loss']
+    for name, _ in ec.variables():
+        gc, gl = ec.get_gradient(name).astype(np.float64), el.get_gradient(name).astype(np.float64)
+        assert np.linalg.norm(gc - gl) <= 1e-3 * max(np.linalg.norm(gl), 1e-30), name
+    ec.close(); el.close()
+
+
+def test_chain_falls_back_when_it_does_not_fit():
+    """[1000, 100] needs more TMEM columns than an SM has: the per-layer GEMMs run, results unchanged."""
+    ocfg, ecfg = make_cfgs(precision='tf32', layers=(1000, 100), tie=False, act='relu')
+    rng = np.random.default_rng(9)
+    X = rng.uniform(0, 1, (256, 320)).astype(np.float32)
+    P = O.init_params(ocfg, rng)
+    e = _engine(ecfg, P, True)
+    r = e.forward(X, recon=True, loss=True)
+    assert e.chain_launches == 0
+    c = O.forward(ocfg, P, X.astype(np.float64), X.astype(np.float64))
+    assert rel_err(r['recon'].cpu().numpy(), c['decoded']) <= 5e-3
+    e.close()
