@@ -1,10 +1,25 @@
 // Device side of the whole-network chain kernel (design notes in chain_tc.cuh).
 #include "chain_tc.cuh"
 #include "gemm_tc_kernel.cuh"
+#include <stdio.h>
 
 namespace mmae {
 
 // ------------------------------------------------------------------ PTX wrappers specific to the chain
+// 20 warps share 4 issue ports and most of them are waiting at any time: a bare try_wait loop re-issues every ~35
+// cycles (measured: 3/4 of all executed instructions were spin iterations), so waits carry a suspend-time hint and
+// the hardware parks the warp until the phase flips.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+  } while (!done);
+}
+#define mbar_wait mbar_wait_parked
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -46,51 +61,93 @@ struct EpiStage {
   uint32_t aux_phase[2];
   uint32_t uses;          // tiles handed to TMA so far (alternates the two buffers)
 };
-__device__ __forceinline__ float4* row_chunk(uint8_t* tile, int lane, int q) {
-  return reinterpret_cast<float4*>(tile + lane * 128 + ((q ^ (lane & 7)) << 4));
+// 1/d for d >= 1 on the FMA pipe: integer-trick seed (12 % error) + 3 Newton steps (6e-8).  The hidden epilogues sit on
+// the critical path of a tile and share the SM's 16-lane MUFU with the output epilogue's exp/log/rcp, so the
+// softsign divide must not queue behind them.
+__device__ __forceinline__ float rcp_nr(float d) {
+  float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
+  r = r * fmaf(-d, r, 2.f);
+  r = r * fmaf(-d, r, 2.f);
+  r = r * fmaf(-d, r, 2.f);
+  return r;
+}
+// .ftz forms: without them every ex2 / lg2 / rcp drags a denormal-rescaling FSETP + FMUL + FSEL sequence along
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <int ACT> __device__ __forceinline__ float act_chain_t(float z) {
+  if (ACT == MMAE_ACT_SOFTSIGN) return z * rcp_ftz(1.f + fabsf(z));
+  return act_fast_t<ACT>(z);
+}
+// log(1 + e) for e in [0, 1]: degree-7 minimax polynomial (max abs error 3e-7), FMA pipe instead of a third MUFU
+__device__ __forceinline__ float log1p_unit(float e) {
+  float r = 0.010243828408420086f;
+  r = fmaf(r, e, -0.053267478942871094f);
+  r = fmaf(r, e, 0.13198965787887573f);
+  r = fmaf(r, e, -0.22396689653396606f);
+  r = fmaf(r, e, 0.327511727809906f);
+  r = fmaf(r, e, -0.4993339478969574f);
+  r = fmaf(r, e, 0.9999702572822571f);
+  return fmaf(r, e, 2.2159764512252877e-07f);
+}
+// Explicit shared-space accesses: through generic pointers the compiler emits LD.E / ST.E and, unable to prove that
+// the bias table and the staging tile do not alias, serialises every load behind the previous store.
+__device__ __forceinline__ uint32_t row_chunk(uint32_t tile_saddr, int lane, int q) {
+  return tile_saddr + lane * 128 + ((q ^ (lane & 7)) << 4);
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {            // ordered with the barriers / stores around it
+  float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ float4 lds128_ro(uint32_t a) {         // read-only table (bias): free to be hoisted
+  float4 v; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v;
 }
 
 // ------------------------------------------------------------------ epilogue of a non-final op, one 32-column chunk
 // v = drop(act(acc + bias)); TMEM <- tf32(v) in place; optional global copy through a swizzled tile + TMA store.
 template <int ACT, bool DROP>
 __device__ __forceinline__ void chain_act_chunk(const ChainOp& o, const CUtensorMap* tmO, uint32_t taddr, int col0, int64_t tile_row0,
-                                                int quad, int lane, const float* bias_s, EpiStage& es) {
+                                                int quad, int lane, uint32_t bias_s, EpiStage& es) {
   uint32_t r[32];
   tc_ld32(taddr, r);
-  uint8_t* tile = es.buf[es.uses & 1];
-  if (o.has_out) {                       // the store issued two tiles ago has finished reading this buffer
-    if (lane == 0) bulk_wait_read<1>();
+  const uint32_t tile = smem_u32(es.buf[0]);
+  if (o.has_out) {                       // the previous store has finished reading the (single) staging tile
+    if (lane == 0) bulk_wait_read<0>();
     __syncwarp();
   }
   const int64_t grow = tile_row0 + quad * 32 + lane + o.ep.row0;      // this thread's global row (dropout stream)
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float4 b = *reinterpret_cast<const float4*>(bias_s + col0 + q * 4);     // warp-uniform address: broadcast
+    const float4 b = lds128_ro(bias_s + (col0 + q * 4) * 4);     // warp-uniform address: broadcast
     float v[4] = {__uint_as_float(r[q * 4 + 0]) + b.x, __uint_as_float(r[q * 4 + 1]) + b.y,
                   __uint_as_float(r[q * 4 + 2]) + b.z, __uint_as_float(r[q * 4 + 3]) + b.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      v[e] = act_fast_t<ACT>(v[e]);
+      v[e] = act_chain_t<ACT>(v[e]);
       if (DROP) {
         uint32_t w = philox_word((uint64_t)grow * (uint64_t)o.ep.drop_width + (uint64_t)(col0 + q * 4 + e), o.ep.drop_stream, o.ep.step, o.ep.seed);
         v[e] = ((w >> 8) < o.ep.keep_thr) ? v[e] / o.ep.keep : 0.f;
       }
       r[q * 4 + e] = to_tf32(v[e]);
     }
-    if (o.has_out) *row_chunk(tile, lane, q) = make_float4(v[0], v[1], v[2], v[3]);
+    if (o.has_out) sts128(row_chunk(tile, lane, q), make_float4(v[0], v[1], v[2], v[3]));
   }
   tc_st32(taddr, r);
   if (o.has_out) {
     fence_async_smem();
     __syncwarp();
-    if (lane == 0) { tma_store_2d(tmO, tile, col0, (int)(tile_row0 + quad * 32)); bulk_commit(); }
+    if (lane == 0) { tma_store_2d(tmO, es.buf[0], col0, (int)(tile_row0 + quad * 32)); bulk_commit(); }
     es.uses++;
   }
 }
 
 template <bool DROP>
 __device__ __forceinline__ void chain_act_dispatch(const ChainOp& o, const CUtensorMap* tmO, uint32_t taddr, int col0, int64_t tile_row0,
-                                                   int quad, int lane, const float* bias_s, EpiStage& es) {
+                                                   int quad, int lane, uint32_t bias_s, EpiStage& es) {
   switch (o.ep.act) {
     case MMAE_ACT_RELU: chain_act_chunk<MMAE_ACT_RELU, DROP>(o, tmO, taddr, col0, tile_row0, quad, lane, bias_s, es); break;
     case MMAE_ACT_TANH: chain_act_chunk<MMAE_ACT_TANH, DROP>(o, tmO, taddr, col0, tile_row0, quad, lane, bias_s, es); break;
@@ -102,53 +159,67 @@ __device__ __forceinline__ void chain_act_dispatch(const ChainOp& o, const CUten
 
 // ------------------------------------------------------------------ epilogue of the final op, one 32-column chunk
 // l = acc + bias; loss += f(l, target); out = dLoss/dl (TRAIN) or decoded_X (PRED).  The target tile was loaded by
-// TMA into `tile`; the result overwrites it in place and leaves with a TMA store.
-template <int MODE, int LOSS>
-__device__ __forceinline__ void chain_final_chunk(const ChainOp& o, uint32_t taddr, int col0, bool row_valid, int lane, const float* bias_s,
-                                                  uint8_t* tile, bool has_aux, float& loss_acc) {
+// TMA into `tile`; the result overwrites it in place and leaves with a TMA store.  AUX = a target is present.
+template <int MODE, int LOSS, bool AUX, bool FULL>
+__device__ __forceinline__ void chain_final_chunk(const ChainOp& o, uint32_t taddr, int col0, bool row_valid, int lane, uint32_t bias_s,
+                                                  uint32_t tile, float& loss_acc) {
   uint32_t r[32];
   tc_ld32(taddr, r);
+  float csum = 0.f;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    float4* cp = row_chunk(tile, lane, q);
-    const float4 b = *reinterpret_cast<const float4*>(bias_s + col0 + q * 4);
-    float4 x4 = has_aux ? *cp : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-    const float bs[4] = {b.x, b.y, b.z, b.w};
-    float outv[4];
+  for (int h = 0; h < 2; ++h) {
+    float4 xq[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float l = __uint_as_float(r[q * 4 + e]) + bs[e], x = xs[e];
-      const bool cnt = has_aux && row_valid && (col0 + q * 4 + e < o.N);
-      float lossv;
-      if (LOSS == MMAE_LOSS_SIGMOID_CE) {
-        const float ex = __expf(-fabsf(l));
-        const float inv = __fdividef(1.f, 1.f + ex);
-        const float s = l >= 0.f ? inv : ex * inv;
-        lossv = fmaxf(l, 0.f) - l * x + __logf(1.f + ex);
-        outv[e] = (MODE == EPI_LOSS_TRAIN) ? (s - x) : s;
-      } else if (LOSS == MMAE_LOSS_RMSE) {
-        const float d = l - x;
-        lossv = d * d;
-        outv[e] = (MODE == EPI_LOSS_TRAIN) ? d : l;
-      } else {
-        lossv = -x * __logf(l);
-        outv[e] = (MODE == EPI_LOSS_TRAIN) ? __fdividef(-x, l) : l;
+    for (int u = 0; u < 4; ++u) xq[u] = AUX ? lds128(row_chunk(tile, lane, h * 4 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = h * 4 + u;
+      const float4 b = lds128_ro(bias_s + (col0 + q * 4) * 4);
+      const float4 x4 = xq[u];
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+      const float bs[4] = {b.x, b.y, b.z, b.w};
+      float outv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float l = __uint_as_float(r[q * 4 + e]) + bs[e], x = xs[e];
+        float lossv = 0.f;
+        if (LOSS == MMAE_LOSS_SIGMOID_CE) {
+          // t = exp(-|l|); sigmoid = 1/(1+t) mirrored for l < 0 with one LOP3 (0.5 + copysign(inv - 0.5, l));
+          // softplus(l) = max(l, 0) + log1p(t), log1p on the FMA pipe: two MUFU ops per element, no predicates
+          const float t = ex2_ftz(fabsf(l) * -1.4426950408889634f);
+          const float inv = rcp_ftz(1.f + t);
+          const float hm = inv - 0.5f;
+          const float sg = __int_as_float((__float_as_int(hm) & 0x7fffffff) | (__float_as_int(l) & 0x80000000));
+          if (AUX) lossv = fmaf(-l, x, fmaxf(l, 0.f)) + log1p_unit(t);
+          outv[e] = (MODE == EPI_LOSS_TRAIN) ? (sg + (0.5f - x)) : (sg + 0.5f);
+        } else if (LOSS == MMAE_LOSS_RMSE) {
+          const float d = l - x;
+          if (AUX) lossv = d * d;
+          outv[e] = (MODE == EPI_LOSS_TRAIN) ? d : l;
+        } else {
+          if (AUX) lossv = -x * __logf(l);
+          outv[e] = (MODE == EPI_LOSS_TRAIN) ? __fdividef(-x, l) : l;
+        }
+        if (AUX) csum += (FULL || col0 + q * 4 + e < o.N) ? lossv : 0.f;
       }
-      if (cnt) loss_acc += lossv;
+      sts128(row_chunk(tile, lane, q), make_float4(outv[0], outv[1], outv[2], outv[3]));
     }
-    *cp = make_float4(outv[0], outv[1], outv[2], outv[3]);
   }
+  if (AUX && row_valid) loss_acc += csum;
 }
 
-template <int MODE>
-__device__ __forceinline__ void chain_final_dispatch(const ChainOp& o, uint32_t taddr, int col0, bool row_valid, int lane, const float* bias_s,
-                                                     uint8_t* tile, bool has_aux, float& loss_acc) {
+template <int MODE, bool AUX>
+__device__ __forceinline__ void chain_final_dispatch(const ChainOp& o, uint32_t taddr, int col0, bool row_valid, int lane, uint32_t bias_s,
+                                                     uint32_t tile, float& loss_acc) {
+  const bool full = col0 + 32 <= o.N;          // warp-uniform: no per-column predicate needed
+#define CH_FINAL(L) do { if (full) chain_final_chunk<MODE, L, AUX, true>(o, taddr, col0, row_valid, lane, bias_s, tile, loss_acc); \
+                         else chain_final_chunk<MODE, L, AUX, false>(o, taddr, col0, row_valid, lane, bias_s, tile, loss_acc); } while (0)
   switch (o.ep.loss) {
-    case MMAE_LOSS_SIGMOID_CE: chain_final_chunk<MODE, MMAE_LOSS_SIGMOID_CE>(o, taddr, col0, row_valid, lane, bias_s, tile, has_aux, loss_acc); break;
-    case MMAE_LOSS_RMSE: chain_final_chunk<MODE, MMAE_LOSS_RMSE>(o, taddr, col0, row_valid, lane, bias_s, tile, has_aux, loss_acc); break;
-    default: chain_final_chunk<MODE, MMAE_LOSS_CE>(o, taddr, col0, row_valid, lane, bias_s, tile, has_aux, loss_acc); break;
+    case MMAE_LOSS_SIGMOID_CE: CH_FINAL(MMAE_LOSS_SIGMOID_CE); break;
+    case MMAE_LOSS_RMSE: CH_FINAL(MMAE_LOSS_RMSE); break;
+    default: CH_FINAL(MMAE_LOSS_CE); break;
   }
+#undef CH_FINAL
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -206,6 +277,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
   if (warp == 0) {
     // ===================== X producer: rows of this CTA's tiles, k-chunk by k-chunk =====================
     if (lane == 0) {
+      if (p.stagger_ns) __nanosleep(((blockIdx.x * 61u) % gridDim.x) * p.stagger_ns);      // spread the CTAs' phases (see chain_tc.cuh)
       int stage = 0; uint32_t phase = 0;
       const int K0 = p.op[0].K;
       for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x) {
@@ -246,6 +318,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
         const ChainOp& o = p.op[i];
         if (i == last && it > 0) { mbar_wait(last_done, par ^ 1); tc_fence_after(); }   // previous tile's result drained
         const uint32_t idesc = idesc_tf32_rt(TC_BM, o.n_chunk);
+        if (p.trace && blockIdx.x == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 0] = clock64();
         for (int nc = 0; nc < o.n_chunks; ++nc) {
           const uint32_t tmem_d = tmem_base + (uint32_t)(o.d_col + nc * o.n_chunk);
           uint32_t accumulate = 0;
@@ -279,102 +352,125 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
           }
         }
         if (lane == 0) tc_commit(&mma_done[i]);
+        if (p.trace && blockIdx.x == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 1] = clock64();
         __syncwarp();
       }
     }
-  } else if (warp >= CH_EPI_WARP0) {
-    // ===================== epilogue warps: quadrant = warp % 4, two warps per quadrant =====================
-    const int ew = warp - CH_EPI_WARP0;
+  } else if (warp >= CH_HID_WARP0 && warp < CH_OUT_WARP0) {
+    // ===================== hidden epilogue warps: non-final ops, activated values back into TMEM =====================
+    const int ew = warp - CH_HID_WARP0;
     const int quad = warp & 3;
     const int half = ew >> 2;
     EpiStage es;
-    es.buf[0] = epi_tiles + ew * 2 * CH_EPI_TILE; es.buf[1] = es.buf[0] + CH_EPI_TILE;
+    es.buf[0] = es.buf[1] = epi_tiles + ew * CH_EPI_TILE;
+    es.aux_bar[0] = es.aux_bar[1] = nullptr; es.aux_phase[0] = es.aux_phase[1] = 0; es.uses = 0;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x, ++it) {
+      const uint32_t par = it & 1;
+      const int64_t tile_row0 = (int64_t)t * TC_BM;
+      for (int i = 0; i < last; ++i) {
+        const ChainOp& o = p.op[i];
+        mbar_wait(&mma_done[i], par);
+        tc_fence_after();
+        if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 2] = clock64();
+        const int chunks = o.n_chunk / 32;
+        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)o.d_col;
+        for (int ch = half; ch < chunks; ch += 2) {
+          if (o.ep.keep < 1.f) chain_act_dispatch<true>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, quad, lane, smem_u32(bias_s + o.bias_off), es);
+          else chain_act_dispatch<false>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, quad, lane, smem_u32(bias_s + o.bias_off), es);
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&chunk_done[i * CH_MAX_CHUNKS + ch]);
+        }
+        if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 3] = clock64();
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every saved activation has landed
+  } else if (warp >= CH_OUT_WARP0) {
+    // ===================== output epilogue warps: the final op (loss, delta_L / decoded_X) =====================
+    const int ew = warp - CH_OUT_WARP0;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    EpiStage es;
+    es.buf[0] = epi_tiles + CH_EPI_WARPS * CH_EPI_TILE + ew * 2 * CH_EPI_TILE; es.buf[1] = es.buf[0] + CH_EPI_TILE;
     es.aux_bar[0] = &aux_bar[ew * 2]; es.aux_bar[1] = &aux_bar[ew * 2 + 1];
     es.aux_phase[0] = es.aux_phase[1] = 0; es.uses = 0;
     float loss_acc = 0.f;
     const ChainOp& lo = p.op[last];
     const bool has_aux = lo.ep.target != nullptr;
     const int lchunks = lo.n_chunks * lo.n_chunk / 32;
+    const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)lo.d_col;
+    const uint32_t lbias = smem_u32(bias_s + lo.bias_off);
     uint32_t it = 0;
     for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x, ++it) {
       const uint32_t par = it & 1;
-      const int64_t tile_row0 = (int64_t)t * TC_BM;
-      const int row0 = (int)(tile_row0 + quad * 32);
-      // ---- non-final ops: activated values back into TMEM (+ optional global copy)
-      for (int i = 0; i < last; ++i) {
-        const ChainOp& o = p.op[i];
-        mbar_wait(&mma_done[i], par);
-        tc_fence_after();
-        const int chunks = o.n_chunk / 32;
-        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)o.d_col;
-        for (int ch = half; ch < chunks; ch += 2) {
-          if (o.ep.keep < 1.f) chain_act_dispatch<true>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, quad, lane, bias_s + o.bias_off, es);
-          else chain_act_dispatch<false>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, quad, lane, bias_s + o.bias_off, es);
-          tc_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&chunk_done[i * CH_MAX_CHUNKS + ch]);
+      const int row0 = (int)((int64_t)t * TC_BM + quad * 32);
+      // the target tile of my first chunk travels while the chain of this tile is still running
+      if (has_aux && half < lchunks && half * 32 < lo.N) {
+        const int b = es.uses & 1;
+        if (lane == 0) {
+          bulk_wait_read<1>();          // the store that last used this buffer is done reading it
+          mbar_expect_tx(es.aux_bar[b], CH_EPI_TILE);
+          tma_load_2d(&p.tmT, es.aux_bar[b], es.buf[b], half * 32, row0);
         }
-      }
-      // ---- final op: the target tile of my first chunk travels while the last MMAs run
-      {
-        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)lo.d_col;
-        if (has_aux && half < lchunks && half * 32 < lo.N) {
-          const int b = es.uses & 1;
-          if (lane == 0) {
-            bulk_wait_read<1>();          // the store that last used this buffer is done reading it
-            mbar_expect_tx(es.aux_bar[b], CH_EPI_TILE);
-            tma_load_2d(&p.tmT, es.aux_bar[b], es.buf[b], half * 32, row0);
-          }
-          __syncwarp();
-        }
-        mbar_wait(&mma_done[last], par);
-        tc_fence_after();
-        const bool row_valid = (int64_t)row0 + lane < p.M;
-        for (int ch = half; ch < lchunks; ch += 2) {
-          if (ch * 32 >= lo.N) break;                                   // padding columns only
-          const int b = es.uses & 1;
-          const int nxt = ch + 2;
-          if (has_aux && nxt < lchunks && nxt * 32 < lo.N) {            // prefetch the next chunk's target tile
-            if (lane == 0) {
-              bulk_wait_read<0>();
-              mbar_expect_tx(es.aux_bar[b ^ 1], CH_EPI_TILE);
-              tma_load_2d(&p.tmT, es.aux_bar[b ^ 1], es.buf[b ^ 1], nxt * 32, row0);
-            }
-            __syncwarp();
-          } else if (!has_aux) {
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
-          }
-          if (has_aux) { mbar_wait(es.aux_bar[b], es.aux_phase[b]); es.aux_phase[b] ^= 1; }
-          uint8_t* tile = es.buf[b];
-          if (lo.ep.mode == EPI_LOSS_TRAIN) chain_final_dispatch<EPI_LOSS_TRAIN>(lo, tbase + ch * 32, ch * 32, row_valid, lane, bias_s + lo.bias_off, tile, has_aux, loss_acc);
-          else chain_final_dispatch<EPI_LOSS_PRED>(lo, tbase + ch * 32, ch * 32, row_valid, lane, bias_s + lo.bias_off, tile, has_aux, loss_acc);
-          __syncwarp();
-          if (lo.ep.colsum_partials && row0 < p.M) {
-            // bias gradient: column sums of this warp's 32 rows, read back column-wise from the swizzled tile
-            const int col = ch * 32 + lane;
-            const int nrows = (int)min((int64_t)32, p.M - row0);
-            float cs = 0.f;
-            for (int r = 0; r < nrows; ++r)
-              cs += *reinterpret_cast<const float*>(tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
-            if (col < lo.N) lo.ep.colsum_partials[(int64_t)(row0 >> 5) * lo.N + col] = cs;
-          }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) { tma_store_2d(&p.tmO[last], tile, ch * 32, row0); bulk_commit(); }
-          es.uses++;
-        }
-        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(last_done);
       }
+      mbar_wait(&mma_done[last], par);
+      tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + last) * 4 + 2] = clock64();
+      const bool row_valid = (int64_t)row0 + lane < p.M;
+      for (int ch = half; ch < lchunks; ch += 2) {
+        if (ch * 32 >= lo.N) break;                                   // padding columns only
+        const int b = es.uses & 1;
+        const int nxt = ch + 2;
+        if (has_aux && nxt < lchunks && nxt * 32 < lo.N) {            // prefetch the next chunk's target tile
+          if (lane == 0) {
+            bulk_wait_read<0>();
+            mbar_expect_tx(es.aux_bar[b ^ 1], CH_EPI_TILE);
+            tma_load_2d(&p.tmT, es.aux_bar[b ^ 1], es.buf[b ^ 1], nxt * 32, row0);
+          }
+          __syncwarp();
+        } else if (!has_aux) {
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+        if (has_aux) { mbar_wait(es.aux_bar[b], es.aux_phase[b]); es.aux_phase[b] ^= 1; }
+        uint8_t* tile_p = es.buf[b];
+        const uint32_t tile = smem_u32(tile_p);
+        if (p.dbg & 1) {} else
+        if (lo.ep.mode == EPI_LOSS_TRAIN) {
+          if (has_aux) chain_final_dispatch<EPI_LOSS_TRAIN, true>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc);
+          else chain_final_dispatch<EPI_LOSS_TRAIN, false>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc);
+        } else {
+          if (has_aux) chain_final_dispatch<EPI_LOSS_PRED, true>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc);
+          else chain_final_dispatch<EPI_LOSS_PRED, false>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc);
+        }
+        __syncwarp();
+        if (lo.ep.colsum_partials && row0 < p.M) {
+          // bias gradient: column sums of this warp's 32 rows, read back column-wise from the swizzled tile
+          const int col = ch * 32 + lane;
+          const int nrows = (int)min((int64_t)32, p.M - row0);
+          float cs = 0.f;
+          for (int r = 0; r < nrows; ++r)
+            cs += lds32(tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+          if (col < lo.N) lo.ep.colsum_partials[(int64_t)(row0 >> 5) * lo.N + col] = cs;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { tma_store_2d(&p.tmO[last], tile_p, ch * 32, row0); bulk_commit(); }
+        es.uses++;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + last) * 4 + 3] = clock64();
+      if (lane == 0) mbar_arrive(last_done);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every output tile has landed
     if (lo.ep.loss_partials) {
       float w = warp_sum(loss_acc);
       if (lane == 0) epi_red[ew] = w;
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps only
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 output warps only
       if (ew == 0 && lane == 0) {
         float sacc = 0.f;
 #pragma unroll

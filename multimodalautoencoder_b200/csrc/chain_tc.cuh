@@ -29,15 +29,19 @@ namespace mmae {
 
 constexpr int CH_MAX_OPS = 8;
 constexpr int CH_MAX_CHUNKS = 8;         // 32-column chunks of a non-final op (N <= 256)
-constexpr int CH_THREADS = 384;          // 12 warps: X producer, W producer, MMA issuer, TMEM owner, 8 epilogue
-constexpr int CH_EPI_WARP0 = 4;
-constexpr int CH_EPI_WARPS = 8;
+// 20 warps: X producer, W producer, MMA issuer, TMEM owner; 8 "hidden" epilogue warps (non-final ops: activations
+// back into TMEM) and 8 "output" epilogue warps (final op: loss + result), so that the output epilogue of tile t runs
+// concurrently with the whole hidden chain of tile t+1.
+constexpr int CH_THREADS = 640;
+constexpr int CH_HID_WARP0 = 4;
+constexpr int CH_OUT_WARP0 = 12;
+constexpr int CH_EPI_WARPS = 8;                  // per group
 constexpr int CH_XSTAGES = 4;
 constexpr int CH_XBYTES = TC_BM * TC_BK * 4;     // 16 KB: [128 rows][32 k]
-constexpr int CH_WRING_BYTES = 88 * 1024;        // weight k-chunks: [n_chunk n][32 k], slot size chosen per launch
+constexpr int CH_WRING_BYTES = 60 * 1024;        // weight k-chunks: [n_chunk n][32 k], slot size chosen per launch
 constexpr int CH_MAX_WSTAGES = 8;
 constexpr int CH_EPI_TILE = 32 * 32 * 4;         // 4 KB: [32 rows][32 cols], 128B swizzle
-constexpr int CH_EPI_BYTES = CH_EPI_WARPS * 2 * CH_EPI_TILE;   // two tiles per epilogue warp
+constexpr int CH_EPI_BYTES = CH_EPI_WARPS * 3 * CH_EPI_TILE;   // one tile per hidden warp, two per output warp
 constexpr int CH_BIAS_FLOATS = 1024;
 constexpr int CH_BAR_BYTES = 1024;
 constexpr int CH_SMEM = CH_XSTAGES * CH_XBYTES + CH_WRING_BYTES + CH_EPI_BYTES + CH_BIAS_FLOATS * 4 + CH_BAR_BYTES + 1024;
@@ -68,6 +72,10 @@ struct ChainParams {
   int w_slot_bytes, w_stages;
   int64_t M;
   int m_tiles;
+  unsigned stagger_ns; // per-CTA start offset step: CTAs that all start together also all load / compute / store together,
+                       // so HBM and L2 see bursts; offsetting them over one tile period smooths the demand (0 = off)
+  int dbg;             // debug switches (MMAE_CHAIN_DBG): 1 = output epilogue skips its math
+  long long* trace;    // debug: clock64 stamps of CTA 0 ([tile it][op][4]: mma start, mma issued, epi start, epi end), or null
 };
 
 // One layer of the chain as the engine describes it: y = epilogue(a . W), W given K-major ([N rows, K cols]).

@@ -557,12 +557,31 @@ struct mmae_engine {
     ChainParams cp;
     if (!chain_build(cp, a, B, F, ls)) return 0;
     const int grid = std::min(cp.m_tiles, num_sms);
+    static const bool want_trace = getenv("MMAE_CHAIN_TRACE") != nullptr;
+    static const int chain_dbg = getenv("MMAE_CHAIN_DBG") ? atoi(getenv("MMAE_CHAIN_DBG")) : 0;
+    cp.dbg = chain_dbg;
+    static const int chain_stagger = getenv("MMAE_CHAIN_STAGGER") ? atoi(getenv("MMAE_CHAIN_STAGGER")) : 60;
+    cp.stagger_ns = cp.m_tiles >= 8 * grid ? (unsigned)chain_stagger : 0u;
+    long long* trace = nullptr;
+    if (want_trace) { cudaMalloc(&trace, 64 * CH_MAX_OPS * 4 * 8); cudaMemsetAsync(trace, 0, 64 * CH_MAX_OPS * 4 * 8, stream); cp.trace = trace; }
     int pr = prof_begin(flops * (double)B);
     if (pr >= 0) { auto& R = prof_recs[pr]; R.m = B; R.n = -1; R.k = -1; R.ta = 0; R.tb = 1; R.splits = 1; }
     cudaError_t e = chain_launch(cp, grid, stream);
     prof_end(pr);
     ++launches; ++chain_launches;
     if (e != cudaSuccess) return cuda_fail(e, "chain launch");
+    if (trace) {      // debug timeline of CTA 0 (MMAE_CHAIN_TRACE=1): clock64 deltas per tile and op
+      std::vector<long long> h(64 * CH_MAX_OPS * 4);
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost); cudaFree(trace);
+      const long long t0 = h[0];
+      for (int it = 0; it < 8 && it * num_sms < cp.m_tiles; ++it)
+        for (int i = 0; i < cp.nops; ++i) {
+          const long long* q = &h[(it * CH_MAX_OPS + i) * 4];
+          fprintf(stderr, "[chain trace] tile %d op %d: mma start %8lld issued %8lld | epi start %8lld end %8lld\n", it, i,
+                  q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0);
+        }
+    }
     cur_emb = mu;
     d_fused = o.train_recon;
     last_gemm_tc = true;

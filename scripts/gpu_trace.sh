@@ -1,0 +1,12 @@
+MMAE_CHAIN_TRACE=1 timeout 300 python - <<'PY' 2>&1 | tail -45
+import os, sys
+sys.path.insert(0, os.getcwd())
+import torch
+src = open('scripts/time_small.py').read().split("for B in [int(x)")[0]
+exec(src)
+B = 2000000
+X = torch.rand((B, 320), device='cuda')
+e = mk(1, B)
+e.forward(X, recon=True, loss=True)
+torch.cuda.synchronize()
+PY
