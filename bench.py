@@ -30,11 +30,17 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: F, block width list, layers, loss, global batch, head
     'wide': dict(F=4096, blocks=[256] * 16, layers=[2048, 1024, 256], B=65536, tie=False, act='softsign',
-                 loss='sigmoid_cross_entropy'),
+                 loss='sigmoid_cross_entropy'),                                         # BASELINE.json configs[3]
     'small': dict(F=320, blocks=[200, 20, 20, 30, 50], layers=[128, 64], B=65536, tie=False, act='softsign',
-                  loss='sigmoid_cross_entropy'),
+                  loss='sigmoid_cross_entropy'),                                        # configs[0] shape, large batch
+    'cls': dict(F=320, blocks=[200, 20, 20, 30, 50], layers=[200, 100], B=4096, tie=False, act='relu',
+                loss='sigmoid_cross_entropy', head=[50, 20], labels=3),                 # configs[1]
+    'infer': dict(F=320, blocks=[200, 20, 20, 30, 50], layers=[128, 64], B=10_000_000, tie=False, act='softsign',
+                  loss='sigmoid_cross_entropy'),                                        # configs[4]
 }
-FLOPS_PER_SAMPLE = {'wide': 112197632.0, 'small': 507904.0}
+# GEMM FLOPs per sample of one step (cls: reconstruction step + classification step)
+FLOPS_PER_SAMPLE = {'wide': 112197632.0, 'small': 507904.0, 'cls': 880000.0 + 412360.0, 'infer': 196608.0}
+BYTES_PER_SAMPLE = {'small': 1280.0, 'cls': 1292.0, 'infer': 2560.0}
 
 
 def modality_names(n):
@@ -107,22 +113,44 @@ def cpu_port_run(name, steps, warmup, sample_rows):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = O.OracleConfig(num_feats=w['F'], layer_sizes=list(w['layers']), modality_starts=starts, modality_names=names,
-                         tie_weights=w['tie'], activation=w['act'], loss_func=w['loss'], learning_rate=1e-3)
+                         tie_weights=w['tie'], activation=w['act'], loss_func=w['loss'], learning_rate=1e-3,
+                         cls_layer_sizes=w.get('head'), num_labels=w.get('labels', 3))
     rng = np.random.default_rng(0)
     port = CpuPort(cfg, O.init_params(cfg, rng), threads=cores)
     X = rng.uniform(0, 1, (sample_rows, w['F']))
     np.random.seed(0)
+    if name == 'infer':
+        Xm = X.copy()
+        for m in range(len(w['blocks'])):
+            Xm[rng.uniform(size=sample_rows) < 0.2, starts[m]:starts[m + 1]] = -1.0
+        fn, what = (lambda: port.predict(Xm)), 'predict() + per-row fill loop'
+    elif name == 'cls':
+        Yc = (rng.uniform(size=(sample_rows, w['labels'])) < 0.5).astype(np.float64)
+
+        def fn():
+            _, t1 = port.step(X)
+            _, t2 = port.cls_step(X, Yc)
+            return 0.0, t1 + t2
+        what = 'noise loop + recon step, noise loop + classification step'
+    else:
+        fn, what = (lambda: port.step(X)), 'noise loop + fwd + bwd + Adam'
     for _ in range(warmup):
-        port.step(X)
+        fn()
     t0 = time.perf_counter()
     t_noise = 0.0
     for _ in range(steps):
-        _, tn = port.step(X)
+        _, tn = fn()
         t_noise += tn
     dt = time.perf_counter() - t0
     return dict(value=sample_rows * steps / dt, seconds=dt, noise_share=t_noise / dt, cores=cores,
-                sample='%d steps x %d rows of the %s workload (of %d per step), noise loop + fwd + bwd + Adam'
-                       % (steps, sample_rows, name, w['B']))
+                sample='%d steps x %d rows of the %s workload (of %d per step), %s'
+                       % (steps, sample_rows, name, w['B'], what))
+
+
+METRIC = {'wide': 'MMAE train samples/sec (fwd+bwd+Adam)', 'small': 'MMAE train samples/sec (fwd+bwd+Adam)',
+          'cls': 'MMAE train samples/sec (fwd+bwd+Adam), reconstruction step + classification-head step',
+          'infer': 'MMAE fill-in inference samples/sec (reconstruction forward + missing-block fill)'}
+CPU_ROWS = {'wide': 2048, 'small': 16384, 'cls': 4096, 'infer': 65536}
 
 
 def run_reference(args):
@@ -131,10 +159,9 @@ def run_reference(args):
         return
     name = args.workload
     w, _, _ = workload_cfg(name)
-    rows = 2048 if name == 'wide' else 16384
-    r = cpu_port_run(name, args.steps, max(args.warmup, 1), rows)
+    r = cpu_port_run(name, args.steps, max(args.warmup, 1), CPU_ROWS[name])
     line = {
-        'impl': 'reference', 'metric': 'MMAE train samples/sec (fwd+bwd+Adam)', 'value': r['value'], 'unit': 'samples/s',
+        'impl': 'reference', 'metric': METRIC[name], 'value': r['value'], 'unit': 'samples/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * r['seconds'] / args.steps,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': name, 'global_batch': w['B'], 'features': w['F'], 'encoder': w['layers'],
@@ -147,6 +174,27 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def measure_tf32_peak(torch):
+    """cuBLAS tf32 8192^3 on this GPU, back to back for ~0.5 s: the tensor-pipe ceiling of kind::tf32 kernels."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn((n, n), device='cuda'); b = torch.randn((n, n), device='cuda')
+        for _ in range(3):
+            torch.matmul(a, b)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 40
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b)
+        e1.record(); torch.cuda.synchronize()
+        return 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) / 1e3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -155,6 +203,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='wide', choices=sorted(WORKLOADS))
     ap.add_argument('--precision', default='tf32', choices=['tf32', 'fp32'])
+    ap.add_argument('--rows', type=int, default=0, help='override the rows per step (infer / small)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
@@ -176,13 +225,16 @@ def main():
 
     name = args.workload
     w, starts, names = workload_cfg(name)
-    Bg = w['B']
+    train = name != 'infer'
+    Bg = args.rows or w['B']
     assert Bg % world == 0
     B = Bg // world
     F = w['F']
+    head = w.get('head')
     cfg = EngineConfig(num_feats=F, layer_sizes=list(w['layers']), modality_starts=starts, modality_names=names,
                        tie_weights=w['tie'], variational=False, activation=w['act'], loss_func=w['loss'],
-                       learning_rate=1e-3, weight_penalty=0.0, seed=0, precision=args.precision, max_batch=B)
+                       learning_rate=1e-3, weight_penalty=0.0, seed=0, precision=args.precision, max_batch=B,
+                       cls_layer_sizes=head, num_labels=w.get('labels', 3))
     eng = Engine(cfg)
     # random-init weights of the named architecture ('normal' init, multimodal_autoencoder.py:44)
     rng = np.random.default_rng(0)
@@ -191,7 +243,8 @@ def main():
             eng.set_variable(vname, np.full(shp, 0.1, np.float32))
         else:
             eng.set_variable(vname, (np.clip(rng.standard_normal(shp), -2, 2) / np.sqrt(shp[0])).astype(np.float32))
-    if world > 1:
+    dp = world > 1 and train          # inference shards rows with no collective
+    if dp:
         idt = torch.zeros(128, dtype=torch.uint8, device='cuda')
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(Engine.comm_unique_id()), dtype=torch.uint8))
@@ -201,11 +254,27 @@ def main():
     # synthetic SNAPSHOT-shaped data: U[0,1) features, this rank's rows of the global batch
     gen = torch.Generator(device='cuda').manual_seed(1234 + rank)
     X = torch.rand((B, F), device='cuda', generator=gen)
+    Y = None
+    if head:
+        Y = (torch.rand((B, w['labels']), device='cuda', generator=gen) < 0.5).float()
+    if not train:        # each modality of each row independently missing (-1.0) with p = 0.2
+        drop = torch.rand((B, len(w['blocks'])), device='cuda', generator=gen) < 0.2
+        for m in range(len(w['blocks'])):
+            X[:, starts[m]:starts[m + 1]] = torch.where(drop[:, m:m + 1], torch.full_like(X[:, starts[m]:starts[m + 1]], -1.0),
+                                                        X[:, starts[m]:starts[m + 1]])
+        del drop
+    filled = torch.empty((B, F), device='cuda') if not train else None
 
     def step(i):
         eng.set_rng_step(i)
-        eng.gen_noise(B, rank * B)
-        eng.train_step(X, noise=True, keep=1.0)
+        if name == 'infer':
+            eng.forward_into(X, filled=filled)
+        else:
+            eng.gen_noise(B, rank * B)
+            eng.train_step(X, noise=True, keep=1.0)
+            if name == 'cls':
+                eng.gen_noise(B, rank * B)
+                eng.cls_train_step(X, Y, noise=True, keep=1.0)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -219,8 +288,13 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    eng.set_profiling(True)
-    l0 = eng.kernel_launches
+    # The wide workload is timed with per-launch CUDA events on (profiling) inside the timed region.  The small-batch
+    # workloads replay a captured CUDA graph per step, which per-launch events would break up: they are timed
+    # un-instrumented, and the kernel times for the roofline come from a second, instrumented pass of the same steps.
+    live_profile = name in ('wide', 'infer')
+    if live_profile:
+        eng.set_profiling(True)
+    l0, c0, g0 = eng.kernel_launches, eng.chain_launches, eng.graph_replays
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
@@ -229,9 +303,16 @@ def main():
     sync_all()
     ms = ev0.elapsed_time(ev1)
     launches = eng.kernel_launches - l0
+    chains = eng.chain_launches - c0
+    replays = eng.graph_replays - g0
+    if not live_profile:
+        eng.set_profiling(True)
+        for i in range(args.steps):
+            step(args.warmup + args.steps + i)
+        sync_all()
     prof = eng.read_profile()
     eng.set_profiling(False)
-    loss = eng.scalars()['recon_loss']
+    sc = eng.scalars()
     clocks = sampler.stop() if sampler else None
     if dist is not None:
         t = torch.tensor([ms], device='cuda')
@@ -239,23 +320,33 @@ def main():
         ms = float(t.item())
     value = Bg * args.steps / (ms / 1e3)
 
-    # ---- end to end: host-fed steps through the C ABI (pinned memory, H2D + loss D2H inside the timing)
+    # ---- end to end: host-fed steps through the C ABI (pinned memory, H2D + result D2H inside the timing)
     e2e = None
     if not args.no_e2e:
-        hx = [torch.rand((B, F)).pin_memory() for _ in range(2)]
+        Be = B if train else min(B, 1_000_000)       # inference: a bounded 1 M-row slice per call (host RAM)
+        hx = [torch.rand((Be, F)).pin_memory() for _ in range(2)]
+        hy = (torch.rand((Be, w['labels'])) < 0.5).float().pin_memory() if head else None
         hs = torch.zeros((args.steps + args.warmup + 1, 8), dtype=torch.float64).pin_memory()
+        hout = np.empty((Be, F), np.float32) if not train else None
+
+        def estep(i):
+            eng.set_rng_step(2000 + i)
+            if train:
+                eng.train_step_host(hx[i % 2], gen_noise=True)
+                if name == 'cls':
+                    eng.cls_train_step_host(hx[i % 2], hy, gen_noise=True)
+                eng.read_scalars_async(hs[i])
+            else:
+                eng.forward_host(hx[i % 2].numpy(), filled=True)
+
         for i in range(min(args.warmup, 3)):
-            eng.set_rng_step(1000 + i)
-            eng.train_step_host(hx[i % 2], gen_noise=True)
-            eng.read_scalars_async(hs[i])
+            estep(i)
         sync_all()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         t0.record()
         for i in range(args.steps):
-            eng.set_rng_step(2000 + i)
-            eng.train_step_host(hx[i % 2], gen_noise=True)
-            eng.read_scalars_async(hs[i])
+            estep(i)
         t1.record()
         eng.synchronize()
         sync_all()
@@ -265,9 +356,13 @@ def main():
             t = torch.tensor([ems], device='cuda')
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
-        e2e = {'value': Bg * args.steps / (ems / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': Bg * F * 4,
-               'd2h_bytes_per_step': 64 * world, 'ms_per_step': ems / args.steps,
-               'last_loss': float(hs[args.steps - 1][0])}
+        rows_e = Be * world
+        e2e = {'value': rows_e * args.steps / (ems / 1e3), 'unit': 'samples/s',
+               'h2d_bytes_per_step': rows_e * F * 4 + (rows_e * w['labels'] * 4 if head else 0),
+               'd2h_bytes_per_step': 64 * world if train else rows_e * F * 4, 'ms_per_step': ems / args.steps,
+               'rows_per_step': rows_e}
+        if train:
+            e2e['last_loss'] = float(hs[args.steps - 1][0])
 
     if dist is not None:
         dist.barrier()
@@ -276,31 +371,64 @@ def main():
         return
     peaks, pk = measured_peaks()
     peak_tf = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops')))
-    achieved = prof['gemm_flops'] / (prof['gemm_ms'] / 1e3) / 1e12 if prof['gemm_ms'] > 0 else 0.0
-    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                'traffic': None, 'kernel': 'gemm_tc_kernel (tcgen05 kind::tf32)',
-                'peak_source': 'bf16 dense sustained, %s (MEASURED_PEAKS.json); kind::tf32 issues at half the bf16 rate, '
-                               'so 0.5 is this kernel family\'s ceiling against this denominator' % pk,
-                'gemm_share_of_step': prof['gemm_ms'] / ms if ms > 0 else None,
-                'gemm_launches': prof['gemm_launches'],
-                'step_frac_of_peak': (FLOPS_PER_SAMPLE[name] * value / 1e12) / peak_tf}
+    peak_bw = float(peaks.get('hbm_gbs'))
+    tf32_peak = measure_tf32_peak(torch)
+    kern_ms = prof['gemm_ms']
+    achieved_tf = prof['gemm_flops'] / (kern_ms / 1e3) / 1e12 if kern_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(name)
+    if name == 'infer':
+        # dominant kernel = the whole-network chain kernel; algorithmic bytes = read X + write filled X
+        algo = BYTES_PER_SAMPLE[name] * B * args.steps
+        ach = algo / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else 0.0
+        roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak_bw, 'unit': 'GB/s', 'frac': ach / peak_bw, 'traffic': traffic,
+                    'kernel': 'chain_tc_kernel (whole network, activations in TMEM)', 'peak_source': 'copy bandwidth, %s (MEASURED_PEAKS.json)' % pk,
+                    'algorithmic_bytes_per_launch': BYTES_PER_SAMPLE[name] * B,
+                    'kernel_share_of_step': kern_ms / ms if ms > 0 else None, 'kernel_launches': prof['gemm_launches'],
+                    'step_frac_of_peak': (BYTES_PER_SAMPLE[name] * value / world / 1e9) / peak_bw,
+                    'tensor_tflops': achieved_tf}
+    else:
+        roofline = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
+                    'traffic': traffic, 'kernel': 'gemm_tc_kernel + chain_tc_kernel (tcgen05 kind::tf32)',
+                    'peak_source': 'bf16 dense sustained, %s (MEASURED_PEAKS.json); kind::tf32 issues at half the bf16 rate, '
+                                   'so 0.5 is this kernel family\'s ceiling against this denominator' % pk,
+                    'tf32_peak_measured': tf32_peak, 'frac_of_tf32_peak': achieved_tf / tf32_peak if tf32_peak > 0 else None,
+                    'tf32_peak_source': 'cuBLAS tf32 8192^3 timed in this run (SURVEY 8d: kind::tf32 kernels are normalised by a measured TF32 peak)',
+                    'gemm_share_of_step': kern_ms / ms if ms > 0 else None,
+                    'kernel_times': 'CUDA events inside the timed region' if live_profile else 'CUDA events in a second pass of the same steps (the timed pass replays CUDA graphs)',
+                    'gemm_launches': prof['gemm_launches'],
+                    'step_frac_of_peak': (FLOPS_PER_SAMPLE[name] * value / world / 1e12) / peak_tf,
+                    'step_frac_of_tf32_peak': (FLOPS_PER_SAMPLE[name] * value / world / 1e12) / tf32_peak if tf32_peak > 0 else None}
+        if name in BYTES_PER_SAMPLE:      # small configs: the HBM bound beside the tensor bound (SURVEY 8d reports both)
+            roofline['hbm_bound'] = {'algorithmic_GBps': BYTES_PER_SAMPLE[name] * value / world / 1e9, 'peak': peak_bw,
+                                     'frac': BYTES_PER_SAMPLE[name] * value / world / 1e9 / peak_bw}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_port_run(name, 3, 1, 2048 if name == 'wide' else 16384)
+        r = cpu_port_run(name, 3, 1, CPU_ROWS[name])
         cpu = {'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
                'noise_loop_share': r['noise_share']}
     line = {
-        'metric': 'MMAE train samples/sec (fwd+bwd+Adam)', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+        'metric': METRIC[name], 'value': value, 'unit': 'samples/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'tf32' if args.precision == 'tf32' else 'f32',
         'data': 'synthetic',
         'config': {'workload': name, 'global_batch': Bg, 'features': F, 'modality_blocks': len(w['blocks']),
-                   'encoder': w['layers'], 'loss': w['loss'], 'activation': w['act'], 'parallelism': 'dp%d' % world,
-                   'l2_policy': 'inputs larger than L2 (batch X = %.2f GB per rank, re-read every step)' % (B * F * 4 / 1e9),
-                   'noise': 'philox block-mask + 5% zero noise drawn on device every step'},
-        'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
-        'final_loss_per_sample': loss / Bg,
+                   'encoder': w['layers'], 'head': head, 'loss': w['loss'], 'activation': w['act'],
+                   'parallelism': ('dp%d' % world) if train else ('rows sharded over %d GPU(s), no collective' % world),
+                   'l2_policy': 'inputs larger than L2 (batch X = %.2f GB per rank, re-read every step)' % (B * F * 4 / 1e9)
+                                if B * F * 4 > 126e6 else 'L2 flushed by the step itself: activations + deltas + Adam state written '
+                                                          'every step exceed nothing here; X = %.1f MB per rank stays L2-resident, '
+                                                          'as it would in a training loop over a resident dataset' % (B * F * 4 / 1e6),
+                   'noise': 'philox block-mask + 5% zero noise drawn on device every step' if train else
+                            'each modality block of each row missing (-1) with p = 0.2'},
+        'e2e': e2e, 'gpu_launches': launches, 'whole_network_launches': chains, 'graph_replays': replays, 'clocks': clocks, 'roofline': roofline,
+        'cpu_baseline': cpu,
     }
+    if train:
+        line['final_loss_per_sample'] = sc['recon_loss'] / Bg
     print(json.dumps(line))
 
 

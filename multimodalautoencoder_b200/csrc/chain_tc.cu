@@ -129,7 +129,7 @@ __device__ __forceinline__ void chain_act_chunk(const ChainOp& o, const CUtensor
     for (int e = 0; e < 4; ++e) {
       v[e] = act_chain_t<ACT>(v[e]);
       if (DROP) {
-        uint32_t w = philox_word((uint64_t)grow * (uint64_t)o.ep.drop_width + (uint64_t)(col0 + q * 4 + e), o.ep.drop_stream, o.ep.step, o.ep.seed);
+        uint32_t w = philox_word((uint64_t)grow * (uint64_t)o.ep.drop_width + (uint64_t)(col0 + q * 4 + e), o.ep.drop_stream, __ldg(o.ep.step), o.ep.seed);
         v[e] = ((w >> 8) < o.ep.keep_thr) ? v[e] / o.ep.keep : 0.f;
       }
       r[q * 4 + e] = to_tf32(v[e]);
@@ -160,9 +160,9 @@ __device__ __forceinline__ void chain_act_dispatch(const ChainOp& o, const CUten
 // ------------------------------------------------------------------ epilogue of the final op, one 32-column chunk
 // l = acc + bias; loss += f(l, target); out = dLoss/dl (TRAIN) or decoded_X (PRED).  The target tile was loaded by
 // TMA into `tile`; the result overwrites it in place and leaves with a TMA store.  AUX = a target is present.
-template <int MODE, int LOSS, bool AUX, bool FULL>
+template <int MODE, int LOSS, bool AUX, bool FULL, bool FILL, bool WL>
 __device__ __forceinline__ void chain_final_chunk(const ChainOp& o, uint32_t taddr, int col0, bool row_valid, int lane, uint32_t bias_s,
-                                                  uint32_t tile, float& loss_acc) {
+                                                  uint32_t tile, float& loss_acc, uint32_t miss, uint32_t lut_s) {
   uint32_t r[32];
   tc_ld32(taddr, r);
   float csum = 0.f;
@@ -179,6 +179,8 @@ __device__ __forceinline__ void chain_final_chunk(const ChainOp& o, uint32_t tad
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
       const float bs[4] = {b.x, b.y, b.z, b.w};
       float outv[4];
+      uint32_t cm4 = 0u;                                   // modality of the 4 columns, one byte each (warp-uniform)
+      if (FILL) asm("ld.shared.u32 %0, [%1];" : "=r"(cm4) : "r"(lut_s + col0 + q * 4));
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float l = __uint_as_float(r[q * 4 + e]) + bs[e], x = xs[e];
@@ -190,30 +192,37 @@ __device__ __forceinline__ void chain_final_chunk(const ChainOp& o, uint32_t tad
           const float inv = rcp_ftz(1.f + t);
           const float hm = inv - 0.5f;
           const float sg = __int_as_float((__float_as_int(hm) & 0x7fffffff) | (__float_as_int(l) & 0x80000000));
-          if (AUX) lossv = fmaf(-l, x, fmaxf(l, 0.f)) + log1p_unit(t);
+          if (WL) lossv = fmaf(-l, x, fmaxf(l, 0.f)) + log1p_unit(t);
           outv[e] = (MODE == EPI_LOSS_TRAIN) ? (sg + (0.5f - x)) : (sg + 0.5f);
         } else if (LOSS == MMAE_LOSS_RMSE) {
           const float d = l - x;
-          if (AUX) lossv = d * d;
+          if (WL) lossv = d * d;
           outv[e] = (MODE == EPI_LOSS_TRAIN) ? d : l;
         } else {
-          if (AUX) lossv = -x * __logf(l);
+          if (WL) lossv = -x * __logf(l);
           outv[e] = (MODE == EPI_LOSS_TRAIN) ? __fdividef(-x, l) : l;
         }
-        if (AUX) csum += (FULL || col0 + q * 4 + e < o.N) ? lossv : 0.f;
+        if (WL) csum += (FULL || col0 + q * 4 + e < o.N) ? lossv : 0.f;
+        if (FILL) outv[e] = ((miss >> ((cm4 >> (8 * e)) & 31u)) & 1u) ? outv[e] : x;
       }
       sts128(row_chunk(tile, lane, q), make_float4(outv[0], outv[1], outv[2], outv[3]));
     }
   }
-  if (AUX && row_valid) loss_acc += csum;
+  if (WL && row_valid) loss_acc += csum;
 }
 
-template <int MODE, bool AUX>
+template <int MODE, bool AUX, bool FILL = false>
 __device__ __forceinline__ void chain_final_dispatch(const ChainOp& o, uint32_t taddr, int col0, bool row_valid, int lane, uint32_t bias_s,
-                                                     uint32_t tile, float& loss_acc) {
+                                                     uint32_t tile, float& loss_acc, uint32_t miss = 0u, uint32_t lut_s = 0u) {
   const bool full = col0 + 32 <= o.N;          // warp-uniform: no per-column predicate needed
-#define CH_FINAL(L) do { if (full) chain_final_chunk<MODE, L, AUX, true>(o, taddr, col0, row_valid, lane, bias_s, tile, loss_acc); \
-                         else chain_final_chunk<MODE, L, AUX, false>(o, taddr, col0, row_valid, lane, bias_s, tile, loss_acc); } while (0)
+#define CH_FINAL(L) do { \
+    if (FILL && !o.ep.loss_partials) { \
+      if (full) chain_final_chunk<MODE, L, AUX, true, FILL, false>(o, taddr, col0, row_valid, lane, bias_s, tile, loss_acc, miss, lut_s); \
+      else chain_final_chunk<MODE, L, AUX, false, FILL, false>(o, taddr, col0, row_valid, lane, bias_s, tile, loss_acc, miss, lut_s); \
+    } else { \
+      if (full) chain_final_chunk<MODE, L, AUX, true, FILL, AUX>(o, taddr, col0, row_valid, lane, bias_s, tile, loss_acc, miss, lut_s); \
+      else chain_final_chunk<MODE, L, AUX, false, FILL, AUX>(o, taddr, col0, row_valid, lane, bias_s, tile, loss_acc, miss, lut_s); \
+    } } while (0)
   switch (o.ep.loss) {
     case MMAE_LOSS_SIGMOID_CE: CH_FINAL(MMAE_LOSS_SIGMOID_CE); break;
     case MMAE_LOSS_RMSE: CH_FINAL(MMAE_LOSS_RMSE); break;
@@ -269,6 +278,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     for (int c = threadIdx.x; c < w; c += CH_THREADS)
       bias_s[o.bias_off + c] = (o.ep.bias && c < o.N) ? __ldg(o.ep.bias + c) : 0.f;
   }
+  uint8_t* lut = reinterpret_cast<uint8_t*>(bias_s + CH_BIAS_FLOATS - 128);          // column -> modality of the final op (fill-in)
+  if (p.op[last].ep.fill_bits)
+    for (int c = threadIdx.x; c < 512; c += CH_THREADS) lut[c] = c < p.op[last].N ? p.op[last].ep.fill_col_mod[c] : 0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -420,6 +432,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
       tc_fence_after();
       if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + last) * 4 + 2] = clock64();
       const bool row_valid = (int64_t)row0 + lane < p.M;
+      const uint32_t miss = (lo.ep.fill_bits && row_valid) ? __ldg(lo.ep.fill_bits + row0 + lane) : 0u;
       for (int ch = half; ch < lchunks; ch += 2) {
         if (ch * 32 >= lo.N) break;                                   // padding columns only
         const int b = es.uses & 1;
@@ -442,6 +455,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
         if (lo.ep.mode == EPI_LOSS_TRAIN) {
           if (has_aux) chain_final_dispatch<EPI_LOSS_TRAIN, true>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc);
           else chain_final_dispatch<EPI_LOSS_TRAIN, false>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc);
+        } else if (lo.ep.fill_bits && has_aux) {
+          chain_final_dispatch<EPI_LOSS_PRED, true, true>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc, miss, smem_u32(lut));
         } else {
           if (has_aux) chain_final_dispatch<EPI_LOSS_PRED, true>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc);
           else chain_final_dispatch<EPI_LOSS_PRED, false>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc);

@@ -149,7 +149,8 @@ inline bool chain_build(ChainParams& p, const float* X, int64_t M, int64_t ldx, 
     if (!make_tmap(&p.tmB[i], l.Wkm, l.N, l.K, l.ldw, TC_BK, o.n_chunk)) return false;
     if (l.out && !make_tmap_io(&p.tmO[i], l.out, M, l.N, l.ldo)) return false;
   }
-  if (bias_off > CH_BIAS_FLOATS) return false;
+  if (bias_off > CH_BIAS_FLOATS - 128) return false;      // the last 512 bytes hold the fill-in column -> modality table
+  if (last.ep.fill_bits && (last.N > 512 || !last.ep.target || last.ep.mode != EPI_LOSS_PRED)) return false;
   if (last.ep.target && !make_tmap_io(&p.tmT, last.ep.target, M, last.N, last.ep.ldt)) return false;
   p.w_slot_bytes = ch_round_up(max_chunk * TC_BK * 4, 1024);
   p.w_stages = std::min(CH_MAX_WSTAGES, CH_WRING_BYTES / p.w_slot_bytes);

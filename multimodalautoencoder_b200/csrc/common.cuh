@@ -113,7 +113,7 @@ struct Epilogue {
   float keep;             // 1.0 = off
   uint32_t keep_thr;      // ceil(keep * 2^24)
   uint32_t drop_stream;   // kStreamDrop + slot
-  uint32_t step;
+  const uint32_t* step;   // device-resident Philox step (StepState)
   uint64_t seed;
   int64_t drop_width;     // logical width of the dropped activation (element = row*width+col)
   int64_t row0;           // global index of local row 0 (data-parallel shards share one stream)
@@ -126,6 +126,10 @@ struct Epilogue {
   // dgrad mode
   const float* saved;     // stored activations h = drop(act(z)), [M, lds]
   int64_t lds;
+  // fill-in (whole-network kernel only, EPI_LOSS_PRED): C = block missing in the input row ? decoded_X : target
+  // (data_funcs.py:310-381); fill_bits[row] has bit m set when modality m of the row is missing
+  const uint32_t* fill_bits;
+  const uint8_t* fill_col_mod;   // [N] column -> modality
 };
 
 // Which auxiliary matrix the epilogue reads at (row, col): the loss target or the saved activation.
@@ -150,7 +154,7 @@ __device__ __forceinline__ float epilogue_apply(const Epilogue& ep, int64_t row,
       float v = acc + bias_v;
       v = FAST ? act_fwd_fast(ep.act, v) : act_fwd(ep.act, v);
       if (ep.keep < 1.f) {
-        uint32_t w = philox_word((uint64_t)(row + ep.row0) * (uint64_t)ep.drop_width + (uint64_t)col, ep.drop_stream, ep.step, ep.seed);
+        uint32_t w = philox_word((uint64_t)(row + ep.row0) * (uint64_t)ep.drop_width + (uint64_t)col, ep.drop_stream, __ldg(ep.step), ep.seed);
         v = ((w >> 8) < ep.keep_thr) ? v / ep.keep : 0.f;
       }
       return v;
@@ -187,7 +191,7 @@ __device__ __forceinline__ float epilogue_apply(const Epilogue& ep, int64_t row,
       float g = ep.beta != 0.f ? acc + ep.beta * c_old : acc;
       float h = aux;
       if (ep.keep < 1.f) {
-        uint32_t w = philox_word((uint64_t)(row + ep.row0) * (uint64_t)ep.drop_width + (uint64_t)col, ep.drop_stream, ep.step, ep.seed);
+        uint32_t w = philox_word((uint64_t)(row + ep.row0) * (uint64_t)ep.drop_width + (uint64_t)col, ep.drop_stream, __ldg(ep.step), ep.seed);
         if ((w >> 8) < ep.keep_thr) { g = g / ep.keep; h = h * ep.keep; } else { return 0.f; }
       }
       return g * act_bwd_from_output(ep.act, h);

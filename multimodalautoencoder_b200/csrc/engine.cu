@@ -119,6 +119,20 @@ struct mmae_engine {
   int64_t* d_idx = nullptr;
   int maxw = 0;
 
+  // ---- per-step state in device memory (kernels.cuh StepState): Philox step, Adam step counts and rates
+  StepState* d_state = nullptr;
+
+  // ---- CUDA graphs of the train steps (small batches are launch-bound: ~60 launches per step)
+  struct GraphKey { int kind; const void* X; const void* Y; const void* T; int64_t B; int noise; float keep; int64_t gb, fr; void* stream;
+    bool operator==(const GraphKey& o) const { return kind == o.kind && X == o.X && Y == o.Y && T == o.T && B == o.B && noise == o.noise && keep == o.keep && gb == o.gb && fr == o.fr && stream == o.stream; } };
+  struct GraphEntry { GraphKey key; int seen = 0; cudaGraphExec_t exec = nullptr; int64_t n_launches = 0, n_chain = 0; int opt = 0;
+    std::vector<char> dirty_after; bool d_fused_after = false, last_tc_after = false; };
+  std::vector<GraphEntry> graphs;
+  cudaStream_t gstream = nullptr;   // graphs cannot be captured on the legacy default stream: a blocking stream of our own
+                                    // keeps the default stream's implicit ordering with the caller's work
+  int graph_mode = -1;
+  int64_t graph_replays = 0;
+
   // ---- RNG / sharding
   uint64_t rng_step = 0;
   uint32_t cur_step = 0;                          // step used by the in-flight forward/backward pair
@@ -194,7 +208,7 @@ struct mmae_engine {
   }
   Epilogue epi(int mode) const {
     Epilogue e; memset(&e, 0, sizeof(e));
-    e.mode = mode; e.keep = 1.f; e.seed = cfg.seed; e.step = cur_step; e.row0 = first_row; return e;
+    e.mode = mode; e.keep = 1.f; e.seed = cfg.seed; e.step = &d_state->step; e.row0 = first_row; return e;
   }
   void set_dropout(Epilogue& e, float keep, uint32_t slot, int64_t width) const {
     e.keep = keep;
@@ -290,6 +304,7 @@ struct mmae_engine {
     }
     CK(cudaMalloc(&d_scalars, MMAE_NUM_SCALARS * 8)); CK(cudaMemset(d_scalars, 0, MMAE_NUM_SCALARS * 8));
     CK(cudaMalloc(&d_sums, 8 * 8)); CK(cudaMemset(d_sums, 0, 64));
+    CK(cudaMalloc(&d_state, sizeof(StepState))); CK(cudaMemset(d_state, 0, sizeof(StepState)));
     for (int o = 0; o < 2; ++o) {
       std::vector<AdamSeg> segs;
       for (auto& v : vars) { AdamSeg s; s.begin = v.off; s.l2 = v.l2[o]; s.pad = 0.f; segs.push_back(s); }
@@ -322,6 +337,7 @@ struct mmae_engine {
   int ensure_cap(int64_t B) {
     if (B <= cap) return 0;
     CK(cudaStreamSynchronize(stream));
+    clear_graphs();
     int64_t nc = std::max<int64_t>(B, cap + cap / 2);
     const int zw = (F + 31) / 32;
     RET(realloc_dev(zero_bits, nc * zw)); RET(realloc_dev(mod_bits, nc)); RET(realloc_dev(miss_bits, nc));
@@ -348,6 +364,7 @@ struct mmae_engine {
     RET(ensure_cap(B));
     if (B <= cap_acts) return 0;
     CK(cudaStreamSynchronize(stream));
+    clear_graphs();
     int64_t nc = std::max<int64_t>(B, cap_acts + cap_acts / 2);
     RET(realloc_dev(noisy, nc * F));
     for (int i = 0; i + 1 < L; ++i) RET(realloc_dev(ea[i], nc * layers[i]));
@@ -362,6 +379,7 @@ struct mmae_engine {
     RET(ensure_cap(B));
     if (B <= cap_host) return 0;
     CK(cudaStreamSynchronize(stream)); CK(cudaStreamSynchronize(copy_stream));
+    clear_graphs();
     int64_t nc = std::max<int64_t>(B, cap_host + cap_host / 2);
     for (int i = 0; i < 2; ++i) { RET(realloc_dev(xin[i], nc * F)); RET(realloc_dev(yin[i], nc * std::max(C, 1))); }
     cap_host = nc;
@@ -371,12 +389,14 @@ struct mmae_engine {
   int ensure_splitk(int64_t count) {
     if (count <= splitk_cap) return 0;
     CK(cudaStreamSynchronize(stream));
+    clear_graphs();
     RET(realloc_dev(splitk_ws, count)); splitk_cap = count; return 0;
   }
 
   void release() {
     auto fr = [](void* p) { if (p) cudaFree(p); };
-    fr(PT); fr(colpart); fr(P); fr(G); fr(M0); fr(V0); fr(M1); fr(V1); fr(d_scalars); fr(d_sums); fr(d_segs[0]); fr(d_segs[1]);
+    clear_graphs();
+    fr(d_state); fr(PT); fr(colpart); fr(P); fr(G); fr(M0); fr(V0); fr(M1); fr(V1); fr(d_scalars); fr(d_sums); fr(d_segs[0]); fr(d_segs[1]);
     fr(d_col_mod); fr(d_starts); fr(zero_bits); fr(mod_bits); fr(miss_bits);
     for (int i = 0; i < 2; ++i) { fr(xin[i]); fr(yin[i]); fr(ds_X[i]); fr(ds_Y[i]); }
     fr(noisy);
@@ -386,6 +406,7 @@ struct mmae_engine {
     for (int i = 0; i < 2; ++i) { if (xin_free[i]) cudaEventDestroy(xin_free[i]); if (xin_ready[i]) cudaEventDestroy(xin_ready[i]); }
     for (auto& r : prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (gstream) cudaStreamDestroy(gstream);
     if (comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(comm); comm = nullptr; }
     for (auto ev : comm_events) cudaEventDestroy(ev);
     if (comm_done) cudaEventDestroy(comm_done);
@@ -493,6 +514,7 @@ struct mmae_engine {
     const float* X; const float* target; const float* labels;
     int64_t B; bool noise; float keep; bool train_recon;   // train_recon: last layer emits delta_L
     bool decoder; bool headp; float* recon_out;
+    float* fill_out = nullptr;     // whole-network kernel: write the filled matrix (A15) instead of decoded_X
   };
 
   int begin_step(int64_t B, bool noise) {
@@ -504,16 +526,95 @@ struct mmae_engine {
     return 0;
   }
 
+  int advance_step() {
+    rng_step += 1;
+    advance_step_kernel<<<1, 1, 0, stream>>>(d_state); CKL("advance_step");
+    return 0;
+  }
+  int set_step(uint64_t step) {
+    rng_step = step;
+    const uint32_t v = (uint32_t)step;
+    CK(cudaMemcpyAsync(&d_state->step, &v, 4, cudaMemcpyHostToDevice, stream));    // pageable source: staged before return
+    return 0;
+  }
+  int set_t(int opt, int64_t t) {
+    t_opt[opt] = t;
+    const long long v = (long long)t;
+    CK(cudaMemcpyAsync(&d_state->t[opt], &v, 8, cudaMemcpyHostToDevice, stream));
+    return 0;
+  }
+
+  // ----------------------------------------------------------------- CUDA graphs
+  // A train step with fixed (input pointer, batch, flags) is the same launch sequence every time once the per-step
+  // scalars live in device memory: the first call runs eagerly (sizes every workspace), the second is captured,
+  // later ones replay one graph launch instead of ~30-70 kernel launches + tensor-map encodes.
+  void clear_graphs() {
+    for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
+  bool graphs_allowed() {
+    if (graph_mode < 0) { const char* ev = getenv("MMAE_GRAPHS"); graph_mode = (ev && ev[0] == '0') ? 0 : 1; }
+    return graph_mode == 1 && !profiling && !dp_on() && !sticky;
+  }
+  template <class Body> int run_graphed(const GraphKey& key, int opt, int64_t B, Body body) {
+    if (!graphs_allowed() || B * (int64_t)F > ((int64_t)1 << 26)) return body();      // large batches are not launch-bound
+    GraphEntry* ge = nullptr;
+    for (auto& g : graphs) if (g.key == key) { ge = &g; break; }
+    if (!ge) {
+      if (graphs.size() >= 16) clear_graphs();
+      GraphEntry n; n.key = key; n.seen = 1; n.opt = opt; graphs.push_back(n);
+      return body();                                             // eager: grows workspaces, configures kernels
+    }
+    if (!stream && !gstream) CK(cudaStreamCreate(&gstream));
+    cudaStream_t cs = stream ? stream : gstream;
+    if (ge->exec) {                                              // replay + the host-side effects of one step
+      rng_step += 1; t_opt[ge->opt] += 1; launches += ge->n_launches; chain_launches += ge->n_chain; last_B = B;
+      pt_dirty = ge->dirty_after; d_fused = ge->d_fused_after; last_gemm_tc = ge->last_tc_after;
+      ++graph_replays;
+      CK(cudaGraphLaunch(ge->exec, cs));
+      return 0;
+    }
+    // capture.  All K-major weight shadows are forced stale so that the graph always refreshes the ones it reads.
+    const size_t idx = (size_t)(ge - graphs.data());
+    std::fill(pt_dirty.begin(), pt_dirty.end(), 1);
+    const int64_t l0 = launches, c0 = chain_launches, cap0 = cap, capa0 = cap_acts, caph0 = cap_host, sk0 = splitk_cap;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) { (void)cudaGetLastError(); graph_mode = 0; return body(); }
+    cudaStream_t user_stream = stream;
+    stream = cs;
+    int r = body();
+    stream = user_stream;
+    ce = cudaStreamEndCapture(cs, &graph);
+    GraphEntry& g = graphs[idx];
+    if (r != 0 || ce != cudaSuccess || !graph || cap != cap0 || cap_acts != capa0 || cap_host != caph0 || splitk_cap != sk0) {
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+      graph_mode = 0; clear_graphs();                            // something in the step is not capturable: stay eager
+      if (r != 0) return r;
+      return fail(MMAE_ERR_CUDA, "graph capture of the train step failed; rerun with MMAE_GRAPHS=0");
+    }
+    ce = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { g.exec = nullptr; graph_mode = 0; return cuda_fail(ce, "cudaGraphInstantiate"); }
+    g.n_launches = launches - l0; g.n_chain = chain_launches - c0;
+    g.dirty_after = pt_dirty; g.d_fused_after = d_fused; g.last_tc_after = last_gemm_tc;
+    CK(cudaGraphLaunch(g.exec, cs));
+    return 0;
+  }
+
   // Whole-network launch (chain_tc.cuh): encoder + decoder + loss in one persistent tcgen05 kernel, activations
   // resident in TMEM.  Returns 1 when it ran, 0 when the configuration does not fit (caller runs the per-layer
   // GEMMs), or a (negative) error code.
   int64_t chain_launches = 0;
   int chain_mode = -1;
+  bool fill_fused = false;       // the last forward wrote the filled matrix from the whole-network kernel
   int forward_chain(const FwdOpts& o, const float* a) {
     if (chain_mode < 0) { const char* ev = getenv("MMAE_CHAIN"); chain_mode = (ev && ev[0] == '0') ? 0 : 1; }
     if (!chain_mode || cfg.precision != MMAE_PREC_TF32 || cfg.variational || o.B < 32) return 0;
     const int64_t B = o.B;
     const bool save = o.train_recon;
+    if (o.fill_out && (o.train_recon || o.noise)) return 0;
     std::vector<ChainLayer> ls;
     double flops = 0.0;
     for (int i = 0; i < L; ++i) {
@@ -550,6 +651,11 @@ struct mmae_engine {
         l.ep.target = o.target; l.ep.ldt = F; l.ep.loss_partials = o.target ? partials : nullptr;
         if (o.train_recon) l.ep.colsum_partials = colpart;
         l.out = dst;
+        if (o.fill_out) {          // fill-in fused into the last epilogue: missing blocks <- decoded_X, the rest <- X
+          if (!o.target) l.ep.target = o.X;
+          l.ep.loss_partials = o.target ? partials : nullptr;
+          l.ep.fill_bits = miss_bits; l.ep.fill_col_mod = d_col_mod; l.out = o.fill_out;
+        }
       }
       l.ldo = dout;
       ls.push_back(l); flops += 2.0 * din * dout;
@@ -585,6 +691,7 @@ struct mmae_engine {
     cur_emb = mu;
     d_fused = o.train_recon;
     last_gemm_tc = true;
+    fill_fused = o.fill_out != nullptr;
     if (o.target) { int r = reduce_partials(grid, 0); if (r) return r; }
     return 1;
   }
@@ -625,7 +732,7 @@ struct mmae_engine {
     cur_emb = mu;
     if (cfg.variational) {
       VaeArgs va; va.mu = mu; va.lv = lv; va.eps = eps; va.emb = emb; va.kl_partials = partials;
-      va.batch = B; va.row0 = first_row; va.E = E; va.step = cur_step; va.seed = cfg.seed; va.gen_eps = eps_injected ? 0 : 1;
+      va.batch = B; va.row0 = first_row; va.E = E; va.step = &d_state->step; va.seed = cfg.seed; va.gen_eps = eps_injected ? 0 : 1;
       int g = grid_for(B * E, 256);
       vae_sample_kernel<<<g, 256, 0, stream>>>(va);
       CKL("vae_sample");
@@ -863,15 +970,16 @@ struct mmae_engine {
   int apply_update(int opt, int64_t B) {
     if (opt == 1 && H == 0) return fail(MMAE_ERR_STATE, "no classification head");
     t_opt[opt] += 1;
-    const double t = (double)t_opt[opt];
     const double lr = opt == 0 ? cfg.learning_rate : cfg.head_learning_rate;
+    adam_prep_kernel<<<1, 1, 0, stream>>>(d_state, opt, lr, (double)cfg.beta1, (double)cfg.beta2);
+    CKL("adam_prep");
     AdamArgs a; a.P = P; a.G = G;
     a.M = opt == 0 ? M0 : M1; a.V = opt == 0 ? V0 : V1;
     a.begin = opt == 0 ? 0 : enc_begin; a.end = opt == 0 ? enc_end : nP;
     a.segs = d_segs[opt]; a.nsegs = nsegs[opt]; a.sums = d_sums;
     a.scale_mode = (opt == 0 && cfg.loss_func == MMAE_LOSS_RMSE) ? 1 : 0;
     a.n_elems = (double)gbatch(B) * F;
-    a.alpha = (float)(lr * sqrt(1.0 - pow((double)cfg.beta2, t)) / (1.0 - pow((double)cfg.beta1, t)));
+    a.alpha = &d_state->alpha[opt];
     a.b1 = cfg.beta1; a.b2 = cfg.beta2; a.eps = cfg.adam_eps; a.scalars_out = d_scalars;
     adam_kernel<<<grid_for(a.end - a.begin, 256), 256, 0, stream>>>(a);
     CKL("adam");
@@ -903,7 +1011,7 @@ int launch_noise_gen(mmae_engine* e, int64_t batch, int64_t first_row) {
   a.mode = e->cfg.noise_mode; a.num_types = (int)e->type_masks.size(); a.num_drop = e->cfg.num_modalities_to_drop;
   for (size_t i = 0; i < e->thresholds.size(); ++i) a.thresholds[i] = e->thresholds[i];
   for (size_t i = 0; i < e->type_masks.size(); ++i) a.type_masks[i] = e->type_masks[i];
-  a.step = (uint32_t)e->rng_step; a.seed = e->cfg.seed;
+  a.step = &e->d_state->step; a.seed = e->cfg.seed;
   const int wpb = 8;
   noise_gen_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(a);
   ++e->launches;
@@ -921,8 +1029,7 @@ int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float kee
   r = e->sums_allreduce(); if (r) return r;          // overlaps the whole backward pass
   r = e->backward_recon(B, keep); if (r) return r;
   e->last_B = B;
-  e->rng_step += 1;
-  return 0;
+  return e->advance_step();
 }
 
 int do_cls(mmae_engine* e, const float* X, const float* Y, int64_t B, int use_noise, float keep) {
@@ -935,8 +1042,7 @@ int do_cls(mmae_engine* e, const float* X, const float* Y, int64_t B, int use_no
   r = e->sums_allreduce(); if (r) return r;
   r = e->backward_cls(B, keep); if (r) return r;
   e->last_B = B;
-  e->rng_step += 1;
-  return 0;
+  return e->advance_step();
 }
 
 // stage a host batch into the double-buffered device input; returns the device pointers
@@ -985,11 +1091,12 @@ void mmae_destroy(mmae_engine* e) {
 
 const char* mmae_last_error(const mmae_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 
-int mmae_set_stream(mmae_engine* e, void* s) { ENTER(e); e->stream = (cudaStream_t)s; return 0; }
+int mmae_set_stream(mmae_engine* e, void* s) { ENTER(e); e->clear_graphs(); e->stream = (cudaStream_t)s; return 0; }
 
 int mmae_synchronize(mmae_engine* e) {
   ENTER(e);
   cudaError_t ce = cudaStreamSynchronize(e->copy_stream);
+  if (ce == cudaSuccess && e->gstream) ce = cudaStreamSynchronize(e->gstream);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
   if (ce != cudaSuccess) return e->cuda_fail(ce, "synchronize");
   return 0;
@@ -1054,11 +1161,11 @@ int mmae_set_opt_state(mmae_engine* e, int opt, const char* name, const float* m
   const int64_t base = opt == 0 ? 0 : e->enc_begin;
   if (m_host) { r = var_copy(e, name, opt == 0 ? e->M0 : e->M1, base, const_cast<float*>(m_host), count, true); if (r) return r; }
   if (v_host) { r = var_copy(e, name, opt == 0 ? e->V0 : e->V1, base, const_cast<float*>(v_host), count, true); if (r) return r; }
-  if (t >= 0) e->t_opt[opt] = t;
+  if (t >= 0) return e->set_t(opt, t);
   return 0;
 }
 
-int mmae_set_rng_step(mmae_engine* e, uint64_t step) { ENTER(e); e->rng_step = step; return 0; }
+int mmae_set_rng_step(mmae_engine* e, uint64_t step) { ENTER(e); return e->set_step(step); }
 
 int mmae_set_noise(mmae_engine* e, const uint32_t* zero_bits_host, const uint32_t* mod_bits_host, int64_t batch) {
   ENTER(e);
@@ -1114,16 +1221,21 @@ int mmae_forward(mmae_engine* e, const float* X_dev, const float* target_dev, co
   o.target = (want & MMAE_WANT_LOSS) ? (target_dev ? target_dev : X_dev) : nullptr;
   o.labels = labels_dev; o.train_recon = false; o.decoder = need_dec; o.headp = need_head;
   o.recon_out = (out && (want & MMAE_WANT_RECON)) ? out->recon : nullptr;
+  e->fill_fused = false;
+  const bool want_fill = (want & MMAE_WANT_FILLED) && out && out->filled;
+  if (want_fill) {       // missing-block detection (data_funcs.py:366-381) runs first so the select can fuse into the last epilogue
+    const int wpb = 8;
+    missing_bits_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(X_dev, batch, e->F, e->d_starts, e->M, e->miss_bits);
+    ++e->launches;
+    if (!(want & MMAE_WANT_RECON) && !use_noise) o.fill_out = out->filled;
+  }
   r = e->forward(o); if (r) return r;
   cudaError_t ce = cudaSuccess;
   if ((want & MMAE_WANT_EMBEDDING) && out && out->embedding)
     ce = cudaMemcpyAsync(out->embedding, e->cur_emb, (size_t)batch * e->E * 4, cudaMemcpyDeviceToDevice, e->stream);
   if (ce != cudaSuccess) return e->cuda_fail(ce, "embedding copy");
-  if ((want & MMAE_WANT_FILLED) && out && out->filled) {
+  if (want_fill && !e->fill_fused) {
     const float* rec = o.recon_out ? o.recon_out : e->out;
-    const int wpb = 8;
-    missing_bits_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(X_dev, batch, e->F, e->d_starts, e->M, e->miss_bits);
-    ++e->launches;
     fill_select_kernel<<<e->grid_for(batch * e->F, 256), 256, 0, e->stream>>>(X_dev, rec, e->miss_bits, e->d_col_mod, out->filled, batch, e->F);
     ++e->launches;
     ce = cudaGetLastError();
@@ -1139,7 +1251,7 @@ int mmae_forward(mmae_engine* e, const float* X_dev, const float* target_dev, co
     }
   }
   r = e->finalize_scalars(batch, (want & MMAE_WANT_LOSS) != 0, (want & MMAE_WANT_HEAD_LOSS) != 0); if (r) return r;
-  if (use_noise || keep < 1.f || e->cfg.variational) e->rng_step += 1;
+  if (use_noise || keep < 1.f || e->cfg.variational) { r = e->advance_step(); if (r) return r; }
   e->last_B = batch;
   return 0;
 }
@@ -1173,28 +1285,53 @@ int mmae_apply_update(mmae_engine* e, int optimizer) {
   return r;
 }
 
-int mmae_train_step(mmae_engine* e, const float* X_dev, int64_t batch, int use_noise, float keep) {
-  ENTER(e);
-  int r = do_train(e, X_dev, batch, use_noise, keep); if (r) return r;
+namespace {
+int train_core(mmae_engine* e, const float* Xd, const float* target, int64_t batch, int use_noise, float keep) {
+  int r = do_train(e, Xd, batch, use_noise, keep, target); if (r) return r;
   r = e->allreduce_grads(); if (r) return r;
   r = e->finalize_scalars(batch, true, false); if (r) return r;
   return e->apply_update(0, batch);
+}
+int cls_core(mmae_engine* e, const float* Xd, const float* Yd, int64_t batch, int use_noise, float keep) {
+  int r = do_cls(e, Xd, Yd, batch, use_noise, keep); if (r) return r;
+  r = e->allreduce_grads(); if (r) return r;
+  r = e->finalize_scalars(batch, false, true); if (r) return r;
+  return e->apply_update(1, batch);
+}
+mmae_engine::GraphKey graph_key(mmae_engine* e, int kind, const void* X, const void* Y, const void* T, int64_t B, int noise, float keep) {
+  mmae_engine::GraphKey k; memset(&k, 0, sizeof(k));
+  k.kind = kind; k.X = X; k.Y = Y; k.T = T; k.B = B; k.noise = noise; k.keep = keep; k.gb = e->global_batch; k.fr = e->first_row;
+  k.stream = (void*)e->stream;
+  return k;
+}
+int train_graphed(mmae_engine* e, const float* Xd, const float* target, int64_t batch, int use_noise, float keep) {
+  if (e->sticky) return e->fail(MMAE_ERR_CUDA, "engine is in a sticky CUDA error state: " + e->err);
+  if (use_noise && e->noise_rows < batch) return train_core(e, Xd, target, batch, use_noise, keep);   // reports the state error
+  return e->run_graphed(graph_key(e, 0, Xd, nullptr, target, batch, use_noise, keep), 0, batch,
+                        [&] { return train_core(e, Xd, target, batch, use_noise, keep); });
+}
+int cls_graphed(mmae_engine* e, const float* Xd, const float* Yd, int64_t batch, int use_noise, float keep) {
+  if (e->H == 0) return e->fail(MMAE_ERR_STATE, "engine was created without a classification head");
+  if (e->sticky) return e->fail(MMAE_ERR_CUDA, "engine is in a sticky CUDA error state: " + e->err);
+  if (use_noise && e->noise_rows < batch) return cls_core(e, Xd, Yd, batch, use_noise, keep);
+  return e->run_graphed(graph_key(e, 1, Xd, Yd, nullptr, batch, use_noise, keep), 1, batch,
+                        [&] { return cls_core(e, Xd, Yd, batch, use_noise, keep); });
+}
+}  // namespace
+
+int mmae_train_step(mmae_engine* e, const float* X_dev, int64_t batch, int use_noise, float keep) {
+  ENTER(e);
+  return train_graphed(e, X_dev, nullptr, batch, use_noise, keep);
 }
 
 int mmae_train_step_pair(mmae_engine* e, const float* X_in_dev, const float* target_dev, int64_t batch, int use_noise, float keep) {
   ENTER(e);
-  int r = do_train(e, X_in_dev, batch, use_noise, keep, target_dev); if (r) return r;
-  r = e->allreduce_grads(); if (r) return r;
-  r = e->finalize_scalars(batch, true, false); if (r) return r;
-  return e->apply_update(0, batch);
+  return train_graphed(e, X_in_dev, target_dev, batch, use_noise, keep);
 }
 
 int mmae_cls_train_step(mmae_engine* e, const float* X_dev, const float* labels_dev, int64_t batch, int use_noise, float keep) {
   ENTER(e);
-  int r = do_cls(e, X_dev, labels_dev, batch, use_noise, keep); if (r) return r;
-  r = e->allreduce_grads(); if (r) return r;
-  r = e->finalize_scalars(batch, false, true); if (r) return r;
-  return e->apply_update(1, batch);
+  return cls_graphed(e, X_dev, labels_dev, batch, use_noise, keep);
 }
 
 int mmae_train_step_host(mmae_engine* e, const float* X_host, int64_t batch, int gen_noise, float keep) {
@@ -1202,11 +1339,8 @@ int mmae_train_step_host(mmae_engine* e, const float* X_host, int64_t batch, int
   float* Xd = nullptr;
   int t = stage_host(e, X_host, nullptr, batch, 0, &Xd, nullptr); if (t < 0) return t;
   if (gen_noise) { int r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }
-  int r = do_train(e, Xd, batch, gen_noise || e->noise_rows >= batch ? (gen_noise ? 1 : 0) : 0, keep); if (r) return r;
-  r = release_stage(e, t); if (r) return r;
-  r = e->allreduce_grads(); if (r) return r;
-  r = e->finalize_scalars(batch, true, false); if (r) return r;
-  return e->apply_update(0, batch);
+  int r = train_graphed(e, Xd, nullptr, batch, gen_noise ? 1 : 0, keep); if (r) return r;
+  return release_stage(e, t);
 }
 
 int mmae_cls_train_step_host(mmae_engine* e, const float* X_host, const float* labels_host, int64_t batch, int gen_noise, float keep) {
@@ -1216,11 +1350,8 @@ int mmae_cls_train_step_host(mmae_engine* e, const float* X_host, const float* l
   const int ycols = e->cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? e->C : 1;
   int t = stage_host(e, X_host, labels_host, batch, ycols, &Xd, &Yd); if (t < 0) return t;
   if (gen_noise) { int r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }
-  int r = do_cls(e, Xd, Yd, batch, gen_noise ? 1 : 0, keep); if (r) return r;
-  r = release_stage(e, t); if (r) return r;
-  r = e->allreduce_grads(); if (r) return r;
-  r = e->finalize_scalars(batch, false, true); if (r) return r;
-  return e->apply_update(1, batch);
+  int r = cls_graphed(e, Xd, Yd, batch, gen_noise ? 1 : 0, keep); if (r) return r;
+  return release_stage(e, t);
 }
 
 int mmae_forward_host(mmae_engine* e, const float* X_host, const float* target_host, const float* labels_host,
@@ -1299,7 +1430,7 @@ int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, 
     if (ce != cudaSuccess) return e->cuda_fail(ce, "H2D indices");
   } else {
     philox_indices_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, e->stream>>>(e->d_idx, batch, e->first_row,
-                                                                                (uint32_t)e->ds_rows[slot], (uint32_t)e->rng_step, e->cfg.seed);
+                                                                                (uint32_t)e->ds_rows[slot], &e->d_state->step, e->cfg.seed);
     ++e->launches;
   }
   const int wpb = 8;
@@ -1351,6 +1482,7 @@ int mmae_set_shard(mmae_engine* e, int64_t global_batch, int64_t first_row) {
 
 int64_t mmae_kernel_launches(const mmae_engine* e) { return e ? e->launches : 0; }
 int64_t mmae_chain_launches(const mmae_engine* e) { return e ? e->chain_launches : 0; }
+int64_t mmae_graph_replays(const mmae_engine* e) { return e ? e->graph_replays : 0; }
 
 int mmae_set_profiling(mmae_engine* e, int on) {
   ENTER(e);

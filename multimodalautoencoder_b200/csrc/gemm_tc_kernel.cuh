@@ -144,14 +144,14 @@ __device__ __forceinline__ void epi_rows(const Epilogue& ep, const EpiRowCtx& c,
         } else if (MODE == EPI_BIAS_ACT) {
           out = act_fast_t<SUB>(acc + c.bias_v);
           if (DROP) {
-            uint32_t w = philox_word((uint64_t)(c.grow0 + i0 + u) * (uint64_t)ep.drop_width + (uint64_t)c.col, ep.drop_stream, ep.step, ep.seed);
+            uint32_t w = philox_word((uint64_t)(c.grow0 + i0 + u) * (uint64_t)ep.drop_width + (uint64_t)c.col, ep.drop_stream, __ldg(ep.step), ep.seed);
             out = ((w >> 8) < ep.keep_thr) ? out / ep.keep : 0.f;
           }
         } else if (MODE == EPI_DGRAD) {
           float g = acc + c.beta * old[u];
           float h = aux[u];
           if (DROP) {
-            uint32_t w = philox_word((uint64_t)(c.grow0 + i0 + u) * (uint64_t)ep.drop_width + (uint64_t)c.col, ep.drop_stream, ep.step, ep.seed);
+            uint32_t w = philox_word((uint64_t)(c.grow0 + i0 + u) * (uint64_t)ep.drop_width + (uint64_t)c.col, ep.drop_stream, __ldg(ep.step), ep.seed);
             if ((w >> 8) < ep.keep_thr) { g = g / ep.keep; h = h * ep.keep; } else { g = 0.f; }
           }
           out = g * dact_t<SUB>(h);

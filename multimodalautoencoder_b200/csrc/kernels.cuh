@@ -15,7 +15,7 @@ struct NoiseGenArgs {
   int num_feats, zw, n_zero, num_mod;
   int mode, num_types, num_drop;
   uint32_t thresholds[8]; uint32_t type_masks[8];
-  uint32_t step; uint64_t seed;
+  const uint32_t* step; uint64_t seed;     // step lives in device memory (StepState) so that captured graphs replay
 };
 
 __global__ void noise_gen_kernel(const NoiseGenArgs a) {
@@ -29,7 +29,7 @@ __global__ void noise_gen_kernel(const NoiseGenArgs a) {
   __syncwarp();
   int q = (a.n_zero + 3) >> 2;                      // Philox counters per row
   for (int c = lane; c < q; c += 32) {
-    Philox4 p = philox4x32((uint64_t)grow * q + c, kStreamZero, a.step, a.seed);
+    Philox4 p = philox4x32((uint64_t)grow * q + c, kStreamZero, __ldg(a.step), a.seed);
     uint32_t wv[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
@@ -41,7 +41,7 @@ __global__ void noise_gen_kernel(const NoiseGenArgs a) {
     }
   }
   if (lane == 0) {
-    Philox4 p = philox4x32((uint64_t)grow, kStreamMod, a.step, a.seed);
+    Philox4 p = philox4x32((uint64_t)grow, kStreamMod, __ldg(a.step), a.seed);
     uint32_t mb = 0u;
     if (a.mode == MMAE_NOISE_INTELLIGENT) {         // categorical over noise types (:689-695)
       int k = 0;
@@ -120,10 +120,10 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int64_t*
 }
 
 __global__ void philox_indices_kernel(int64_t* idx, int64_t batch, int64_t first, uint32_t n_rows,
-                                      uint32_t step, uint64_t seed) {
+                                      const uint32_t* step, uint64_t seed) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch) return;
-  idx[i] = (int64_t)mulhi_u32(philox_word((uint64_t)(i + first), kStreamBatch, step, seed), n_rows);
+  idx[i] = (int64_t)mulhi_u32(philox_word((uint64_t)(i + first), kStreamBatch, __ldg(step), seed), n_rows);
 }
 
 // ------------------------------------------------------------------ column sums (bias gradients)
@@ -186,7 +186,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int64
 // ------------------------------------------------------------------ VAE (:372-375, :402-406)
 struct VaeArgs {
   const float* mu; const float* lv; float* eps; float* emb; float* kl_partials;
-  int64_t batch, row0; int E; uint32_t step; uint64_t seed; int gen_eps;
+  int64_t batch, row0; int E; const uint32_t* step; uint64_t seed; int gen_eps;
 };
 __global__ void vae_sample_kernel(const VaeArgs a) {
   __shared__ float red[8];
@@ -195,7 +195,7 @@ __global__ void vae_sample_kernel(const VaeArgs a) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     float e;
     if (a.gen_eps) {
-      Philox4 p = philox4x32((uint64_t)(i + a.row0 * a.E), kStreamEps, a.step, a.seed);
+      Philox4 p = philox4x32((uint64_t)(i + a.row0 * a.E), kStreamEps, __ldg(a.step), a.seed);
       float u1 = ((float)(p.x >> 8) + 1.0f) * (1.0f / 16777216.0f);
       float u2 = (float)(p.y >> 8) * (1.0f / 16777216.0f);
       e = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
@@ -292,13 +292,15 @@ struct AdamArgs {
   const double* sums;            // device scalars (loss sums after the optional allreduce)
   int scale_mode;                // 0: 1.0   1: RMSE 1/sqrt(N*sumsq), N = n_elems
   double n_elems;
-  float alpha, b1, b2, eps;
+  const float* alpha;            // lr * sqrt(1 - b2^t) / (1 - b1^t), written by adam_prep_kernel for this step
+  float b1, b2, eps;
   double* scalars_out;           // MMAE_S_* slots, written by thread 0
 };
 __global__ void adam_kernel(const AdamArgs a) {
   float scale = 1.f;
   if (a.scale_mode == 1) scale = (float)(1.0 / sqrt(a.n_elems * a.sums[0]));
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.scalars_out) a.scalars_out[MMAE_S_GRAD_SCALE] = scale;
+  const float alpha = __ldg(a.alpha);
   int64_t n = a.end - a.begin;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t gi = a.begin + i;
@@ -310,25 +312,48 @@ __global__ void adam_kernel(const AdamArgs a) {
     m += (g - m) * (1.f - a.b1);
     v += (g * g - v) * (1.f - a.b2);
     a.M[i] = m; a.V[i] = v;
-    a.P[gi] = p - a.alpha * m / (sqrtf(v) + a.eps);
+    a.P[gi] = p - alpha * m / (sqrtf(v) + a.eps);
   }
+}
+
+// Per-step state kept in DEVICE memory so that a captured CUDA graph of the train step replays unchanged: the Philox
+// step index every random draw is keyed by, and the two optimizers' step counts with their bias-corrected rates.
+struct StepState { uint32_t step; uint32_t pad; long long t[2]; float alpha[2]; };
+__global__ void advance_step_kernel(StepState* s) { s->step += 1u; }
+__global__ void adam_prep_kernel(StepState* s, int opt, double lr, double b1, double b2) {
+  const long long t = ++s->t[opt];                      // TF ApplyAdam: t starts at 1 (:411, :443)
+  s->alpha[opt] = (float)(lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t)));
 }
 
 // ------------------------------------------------------------------ fill-in (data_funcs.py:310-381)
 // miss[r] bit m set iff sum(x[r, s_m:e_m]) == -(e_m - s_m); one warp per row, lanes stride the block.
 __global__ void missing_bits_kernel(const float* __restrict__ X, int64_t batch, int num_feats,
                                     const int32_t* __restrict__ starts, int num_mod, uint32_t* __restrict__ miss) {
+  // one warp per row; 256 columns per pass, all 8 loads of a lane in flight before any reduction.  Modalities are
+  // contiguous column ranges in increasing order, so one running carry covers a block that spans passes.
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= batch) return;
   const float* x = X + row * (int64_t)num_feats;
   uint32_t bits = 0u;
-  for (int m = 0; m < num_mod; ++m) {
-    int s = starts[m], e = starts[m + 1];
-    float t = 0.f;
-    for (int c = s + lane; c < e; c += 32) t += __ldg(x + c);
-    t = warp_sum(t);
-    if (t == -(float)(e - s)) bits |= 1u << m;
+  int m = 0;
+  float carry = 0.f;
+  for (int p0 = 0; p0 < num_feats && m < num_mod; p0 += 256) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const int c = p0 + e * 32 + lane; v[e] = c < num_feats ? __ldg(x + c) : 0.f; }
+    const int pend = min(num_feats, p0 + 256);
+    while (m < num_mod && starts[m] < pend) {
+      const int s = starts[m], e1 = starts[m + 1];
+      float part = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const int c = p0 + e * 32 + lane; part += (c >= s && c < e1) ? v[e] : 0.f; }
+      part = warp_sum(part);
+      if (e1 <= pend) {
+        if (carry + part == -(float)(e1 - s)) bits |= 1u << m;
+        carry = 0.f; ++m;
+      } else { carry += part; break; }
+    }
   }
   if (lane == 0) miss[row] = bits;
 }

@@ -273,6 +273,27 @@ class Engine:
         res['_keepalive'] = (X, tgt, lab)
         return res
 
+    def forward_into(self, X, recon=None, filled=None, embedding=None, loss=False, target=None):
+        """forward() writing into caller-owned device tensors (no allocation inside the call)."""
+        X = self._dev(X)
+        want = 0
+        o = capi.Outputs()
+        if recon is not None:
+            want |= capi.WANT_RECON
+            o.recon = recon.data_ptr()
+        if filled is not None:
+            want |= capi.WANT_FILLED
+            o.filled = filled.data_ptr()
+        if embedding is not None:
+            want |= capi.WANT_EMBEDDING
+            o.embedding = embedding.data_ptr()
+        if loss:
+            want |= capi.WANT_LOSS
+        tgt = None if target is None else self._dev(target)
+        self._ck(self.lib.mmae_forward(self._h, C.c_void_p(X.data_ptr()),
+                                       C.c_void_p(tgt.data_ptr()) if tgt is not None else None, None,
+                                       X.shape[0], 0, 1.0, want, C.byref(o)))
+
     def train_step(self, X, noise=False, keep=1.0):
         X = self._dev(X)
         self._ck(self.lib.mmae_train_step(self._h, C.c_void_p(X.data_ptr()), X.shape[0], int(bool(noise)), float(keep)))
@@ -426,6 +447,11 @@ class Engine:
     @property
     def kernel_launches(self):
         return self.lib.mmae_kernel_launches(self._h)
+
+    @property
+    def graph_replays(self):
+        """Train steps replayed from a captured CUDA graph."""
+        return self.lib.mmae_graph_replays(self._h)
 
     @property
     def chain_launches(self):

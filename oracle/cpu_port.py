@@ -87,4 +87,38 @@ class CpuPort:
                 self.m[k] += (g - self.m[k]) * (1 - c.beta1)
                 self.v[k] += (g * g - self.v[k]) * (1 - c.beta2)
                 p -= a * self.m[k] / (torch.sqrt(self.v[k]) + c.adam_eps)
-        return float(rec), t_noise
+        return float(rec.detach()), t_noise
+
+    def forward_only(self, X):
+        with torch.no_grad():
+            cfg, P = self.cfg, self.P
+            h = X
+            for i in range(cfg.L):
+                h = h @ P['weights%d' % i] + P['encode_biases%d' % i]
+                if i < cfg.L - 1:
+                    h = self._act(h)
+            for j in range(cfg.L):
+                i = cfg.L - 1 - j
+                W = P['weights%d' % i].t() if cfg.tie_weights else P['decode_weights%d' % i]
+                h = h @ W + P['decode_biases%d' % i]
+                if j < cfg.L - 1:
+                    h = self._act(h)
+            return torch.sigmoid(h) if cfg.loss_func == 'sigmoid_cross_entropy' else h
+
+    def predict(self, X64):
+        """fill_missing_data_in_file (:1167-1187): predict() over the whole matrix, then the reference's per-row
+        fill loop (data_funcs.py:310-381).  Returns (filled, 0.0)."""
+        Xbar = self.forward_only(torch.from_numpy(np.asarray(X64, np.float32))).numpy().astype(np.float64)
+        return O.fill_missing(self.cfg, np.asarray(X64, np.float64), Xbar), 0.0
+
+    def cls_step(self, X64, Y64, rng=np.random):
+        """session.run([classification_opt_step]) (:647) on the fp64 oracle graph (NumPy BLAS threads): noise loop,
+        encoder + head forward, head loss, backward, second Adam.  Returns (loss, seconds in the noise loop)."""
+        if not hasattr(self, '_cls_state'):
+            self._cls_state = O.AdamState()
+            self._P64 = {k: v.detach().numpy().astype(np.float64) for k, v in self.P.items()}
+        t0 = time.perf_counter()
+        noisy = O.add_noise(self.cfg, X64, rng)
+        t_noise = time.perf_counter() - t0
+        c, _ = O.cls_train_step(self.cfg, self._P64, self._cls_state, noisy, Y64)
+        return float(c['cls_loss']) if 'cls_loss' in c else 0.0, t_noise

@@ -104,3 +104,32 @@ def test_chain_falls_back_when_it_does_not_fit():
     c = O.forward(ocfg, P, X.astype(np.float64), X.astype(np.float64))
     assert rel_err(r['recon'].cpu().numpy(), c['decoded']) <= 5e-3
     e.close()
+
+
+@pytest.mark.parametrize('with_loss', [False, True])
+def test_chain_fused_fill_in(with_loss):
+    """fill_missing_data_in_file (:1167-1187 + data_funcs.py:310-381) as ONE pass: missing-block detection, then the
+    whole-network kernel whose last epilogue writes decoded_X into missing blocks and the input everywhere else.
+    Untouched cells are bit-exact; filled cells follow the oracle within the tf32 tolerance."""
+    ocfg, ecfg = make_cfgs(precision='tf32', tie=False)
+    B = 1000
+    rng = np.random.default_rng(10)
+    X = rng.uniform(0, 1, (B, 320))
+    P = O.init_params(ocfg, rng)
+    drop = rng.uniform(size=(B, 5)) < 0.2
+    for m in range(5):
+        X[drop[:, m], ocfg.modality_starts[m]:ocfg.modality_starts[m + 1]] = -1.0
+    e = _engine(ecfg, P, True)
+    n0, k0 = e.chain_launches, e.kernel_launches
+    r = e.forward(X.astype(np.float32), filled=True, loss=with_loss)
+    assert e.chain_launches == n0 + 1
+    assert e.kernel_launches - k0 <= 4, 'fill-in should be: missing bits + whole-network kernel (+ loss reduction, scalars)'
+    c = O.forward(ocfg, P, X, X)
+    want = O.fill_missing(ocfg, X, c['decoded'])
+    got = r['filled'].cpu().numpy()
+    keep_mask = np.repeat(~drop, np.diff(ocfg.modality_starts), axis=1)
+    assert np.array_equal(got[keep_mask], X.astype(np.float32)[keep_mask])
+    assert rel_err(got, want) <= 5e-3
+    if with_loss:
+        assert abs(e.scalars()['recon_loss'] - c['recon_loss']) <= 1e-3 * c['recon_loss']
+    e.close()
