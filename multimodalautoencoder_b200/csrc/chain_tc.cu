@@ -20,6 +20,19 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
   } while (!done);
 }
 #define mbar_wait mbar_wait_parked
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar_saddr), "r"(parity), "r"(0x989680u) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tc_commit_s(uint32_t bar_saddr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_saddr) : "memory");
+}
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -45,9 +58,22 @@ __device__ __forceinline__ uint32_t to_tf32(float v) {
 __host__ __device__ inline uint32_t idesc_tf32_rt(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// L2 policies: rows of X are read twice per tile (operand of the first layer, then loss target / fill-in source) and
+// the weights by every tile -> evict_last; the second read of X and all outputs are streaming -> evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void tma_load_2d_hint(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* tm, const void* src, int c0, int c1, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -236,13 +262,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* xring = smem;
-  uint8_t* wring = xring + CH_XSTAGES * CH_XBYTES;
-  uint8_t* epi_tiles = wring + CH_WRING_BYTES;
-  float* bias_s = reinterpret_cast<float*>(epi_tiles + CH_EPI_BYTES);
+  uint8_t* wring = xring + p.x_stages * CH_XBYTES;
+  uint8_t* hid_tiles = xring + CH_POOL_BYTES - CH_HID_BYTES;       // only used (and reserved) when p.hid_tiles
+  uint8_t* out_tiles = xring + CH_POOL_BYTES;
+  float* bias_s = reinterpret_cast<float*>(out_tiles + CH_OUT_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + CH_BIAS_FLOATS * 4);
-  uint64_t* xfull = bars;                               // [CH_XSTAGES]
-  uint64_t* xempty = xfull + CH_XSTAGES;                // [CH_XSTAGES]
-  uint64_t* wfull = xempty + CH_XSTAGES;                // [CH_MAX_WSTAGES]
+  uint64_t* xfull = bars;                               // [CH_MAX_XSTAGES]
+  uint64_t* xempty = xfull + CH_MAX_XSTAGES;            // [CH_MAX_XSTAGES]
+  uint64_t* wfull = xempty + CH_MAX_XSTAGES;            // [CH_MAX_WSTAGES]
   uint64_t* wempty = wfull + CH_MAX_WSTAGES;            // [CH_MAX_WSTAGES]
   uint64_t* mma_done = wempty + CH_MAX_WSTAGES;         // [CH_MAX_OPS]      accumulator of op i complete
   uint64_t* chunk_done = mma_done + CH_MAX_OPS;         // [CH_MAX_OPS][CH_MAX_CHUNKS]  32 activated columns back in TMEM
@@ -259,7 +286,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     for (int i = 0; i < p.nops; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB[i]) : "memory");
   }
   if (warp == 2 && lane == 0) {
-    for (int s = 0; s < CH_XSTAGES; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
+    for (int s = 0; s < CH_MAX_XSTAGES; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
     for (int s = 0; s < CH_MAX_WSTAGES; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int i = 0; i < CH_MAX_OPS; ++i) mbar_init(&mma_done[i], 1);
     for (int i = 0; i < CH_MAX_OPS * CH_MAX_CHUNKS; ++i) mbar_init(&chunk_done[i], 4);     // one warp per lane quadrant
@@ -292,12 +319,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
       if (p.stagger_ns) __nanosleep(((blockIdx.x * 61u) % gridDim.x) * p.stagger_ns);      // spread the CTAs' phases (see chain_tc.cuh)
       int stage = 0; uint32_t phase = 0;
       const int K0 = p.op[0].K;
+      const uint64_t pol_keep = l2_policy_evict_last();
       for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x) {
         for (int k = 0; k < K0; k += TC_BK) {
           mbar_wait(&xempty[stage], phase ^ 1);
           mbar_expect_tx(&xfull[stage], CH_XBYTES);
-          tma_load_2d(&p.tmA, &xfull[stage], xring + stage * CH_XBYTES, k, t * TC_BM);
-          if (++stage == CH_XSTAGES) { stage = 0; phase ^= 1; }
+          tma_load_2d_hint(&p.tmA, &xfull[stage], xring + stage * CH_XBYTES, k, t * TC_BM, pol_keep);
+          if (++stage == p.x_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -305,16 +333,27 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     // ===================== W producer: every op's weight k-chunks, once per tile (L2-resident) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      const uint64_t pol_keep = l2_policy_evict_last();
+      const int nops = p.nops, w_stages = p.w_stages;
+      const uint32_t w_slot = (uint32_t)p.w_slot_bytes;
+      const uint32_t wring_s = smem_u32(wring), wfull_s = smem_u32(wfull), wempty_s = smem_u32(wempty);
+      int opK[CH_MAX_OPS], opNC[CH_MAX_OPS], opNCs[CH_MAX_OPS];
+#pragma unroll
+      for (int i = 0; i < CH_MAX_OPS; ++i) { opK[i] = p.op[i].K; opNC[i] = p.op[i].n_chunk; opNCs[i] = p.op[i].n_chunks; }
       for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x) {
-        for (int i = 0; i < p.nops; ++i) {
-          const ChainOp& o = p.op[i];
-          const uint32_t bytes = (uint32_t)o.n_chunk * TC_BK * 4;
-          for (int nc = 0; nc < o.n_chunks; ++nc) {
-            for (int k = 0; k < o.K; k += TC_BK) {
-              mbar_wait(&wempty[stage], phase ^ 1);
-              mbar_expect_tx(&wfull[stage], bytes);
-              tma_load_2d(&p.tmB[i], &wfull[stage], wring + stage * p.w_slot_bytes, k, nc * o.n_chunk);
-              if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
+#pragma unroll
+        for (int i = 0; i < CH_MAX_OPS; ++i) {
+          if (i < nops) {
+            const uint32_t bytes = (uint32_t)opNC[i] * TC_BK * 4;
+            for (int nc = 0; nc < opNCs[i]; ++nc) {
+              for (int k = 0; k < opK[i]; k += TC_BK) {
+                mbar_wait_s(wempty_s + stage * 8u, phase ^ 1);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wfull_s + stage * 8u), "r"(bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                    ::"r"(wring_s + stage * w_slot), "l"(&p.tmB[i]), "r"(wfull_s + stage * 8u), "r"(k), "r"(nc * opNC[i]), "l"(pol_keep) : "memory");
+                if (++stage == w_stages) { stage = 0; phase ^= 1; }
+              }
             }
           }
         }
@@ -322,50 +361,59 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     }
   } else if (warp == 2) {
     // ===================== MMA issuer =====================
-    int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x, ++it) {
-      const uint32_t par = it & 1;
-      for (int i = 0; i < p.nops; ++i) {
-        const ChainOp& o = p.op[i];
-        if (i == last && it > 0) { mbar_wait(last_done, par ^ 1); tc_fence_after(); }   // previous tile's result drained
-        const uint32_t idesc = idesc_tf32_rt(TC_BM, o.n_chunk);
-        if (p.trace && blockIdx.x == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 0] = clock64();
-        for (int nc = 0; nc < o.n_chunks; ++nc) {
-          const uint32_t tmem_d = tmem_base + (uint32_t)(o.d_col + nc * o.n_chunk);
-          uint32_t accumulate = 0;
-          for (int k = 0; k < o.K; k += TC_BK) {
-            if (o.a_tmem && nc == 0) mbar_wait(&chunk_done[(i - 1) * CH_MAX_CHUNKS + (k >> 5)], par);   // A columns [k, k+32) written
-            mbar_wait(&wfull[ws], wph);
-            if (!o.a_tmem) mbar_wait(&xfull[xs], xph);
-            tc_fence_after();
-            if (lane == 0) {
-              const uint32_t sb = smem_u32(wring + ws * p.w_slot_bytes);
-              const int ksteps = min(TC_BK / TC_UMMA_K, (o.K - k + TC_UMMA_K - 1) / TC_UMMA_K);
-              if (o.a_tmem) {
-                const uint32_t ta = tmem_base + (uint32_t)(o.a_col + k);
-                for (int kk = 0; kk < ksteps; ++kk) {
-                  tc_mma_tf32_ts(tmem_d, ta + kk * TC_UMMA_K, make_smem_desc(sb + kk * 32, 16, 1024), idesc, accumulate);
-                  accumulate = 1;
-                }
+    // One lane runs the whole loop (the rest of the warp parks at the final barrier): its instruction stream is
+    // serial and shares an issue port with four busy epilogue warps, so every per-chunk instruction counts --
+    // per-op fields are hoisted out of the constant bank, descriptors are built by adding to a precomputed base.
+    if (lane == 0) {
+      const uint32_t w_slot = (uint32_t)p.w_slot_bytes;
+      const int w_stages = p.w_stages, x_stages = p.x_stages, nops = p.nops;
+      const uint32_t wring_s = smem_u32(wring), xring_s = smem_u32(xring);
+      const uint64_t desc_hi = make_smem_desc(0, 16, 1024);            // K-major SW128: LBO 16 B, SBO 1024 B; address field added below
+      const uint32_t xfull_s = smem_u32(xfull), xempty_s = smem_u32(xempty), wfull_s = smem_u32(wfull), wempty_s = smem_u32(wempty);
+      int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x, ++it) {
+        const uint32_t par = it & 1;
+        for (int i = 0; i < nops; ++i) {
+          const int K = p.op[i].K, a_tmem = p.op[i].a_tmem, n_chunk = p.op[i].n_chunk, n_chunks = p.op[i].n_chunks;
+          const uint32_t d_col = (uint32_t)p.op[i].d_col, a_col = (uint32_t)p.op[i].a_col;
+          if (i == last && it > 0) { mbar_wait(last_done, par ^ 1); tc_fence_after(); }   // previous tile's result drained
+          const uint32_t idesc = idesc_tf32_rt(TC_BM, n_chunk);
+          const uint32_t cd_s = smem_u32(&chunk_done[(i > 0 ? i - 1 : 0) * CH_MAX_CHUNKS]);
+          if (p.trace && blockIdx.x == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 0] = clock64();
+          for (int nc = 0; nc < n_chunks; ++nc) {
+            const uint32_t tmem_d = tmem_base + d_col + (uint32_t)(nc * n_chunk);
+            uint32_t accumulate = 0;
+            for (int k = 0; k < K; k += TC_BK) {
+              if (a_tmem && nc == 0) mbar_wait_s(cd_s + (uint32_t)(k >> 5) * 8u, par);    // A columns [k, k+32) written
+              mbar_wait_s(wfull_s + ws * 8u, wph);
+              if (!a_tmem) mbar_wait_s(xfull_s + xs * 8u, xph);
+              tc_fence_after();
+              const uint64_t bdesc = desc_hi | (uint64_t)(((wring_s + ws * w_slot) >> 4) & 0x3FFF);
+              const int rem = K - k;
+              if (a_tmem) {
+                const uint32_t ta = tmem_base + a_col + (uint32_t)k;
+                tc_mma_tf32_ts(tmem_d, ta, bdesc, idesc, accumulate);
+                if (rem > 8) tc_mma_tf32_ts(tmem_d, ta + 8, bdesc + 2, idesc, 1);
+                if (rem > 16) tc_mma_tf32_ts(tmem_d, ta + 16, bdesc + 4, idesc, 1);
+                if (rem > 24) tc_mma_tf32_ts(tmem_d, ta + 24, bdesc + 6, idesc, 1);
               } else {
-                const uint32_t sa = smem_u32(xring + xs * CH_XBYTES);
-                for (int kk = 0; kk < ksteps; ++kk) {
-                  tc_mma_tf32(tmem_d, make_smem_desc(sa + kk * 32, 16, 1024), make_smem_desc(sb + kk * 32, 16, 1024), idesc, accumulate);
-                  accumulate = 1;
-                }
-                tc_commit(&xempty[xs]);
+                const uint64_t adesc = desc_hi | (uint64_t)(((xring_s + xs * CH_XBYTES) >> 4) & 0x3FFF);
+                tc_mma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+                if (rem > 8) tc_mma_tf32(tmem_d, adesc + 2, bdesc + 2, idesc, 1);
+                if (rem > 16) tc_mma_tf32(tmem_d, adesc + 4, bdesc + 4, idesc, 1);
+                if (rem > 24) tc_mma_tf32(tmem_d, adesc + 6, bdesc + 6, idesc, 1);
+                tc_commit_s(xempty_s + xs * 8u);
+                if (++xs == x_stages) { xs = 0; xph ^= 1; }
               }
-              tc_commit(&wempty[ws]);
+              accumulate = 1;
+              tc_commit_s(wempty_s + ws * 8u);
+              if (++ws == w_stages) { ws = 0; wph ^= 1; }
             }
-            __syncwarp();
-            if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
-            if (!o.a_tmem) { if (++xs == CH_XSTAGES) { xs = 0; xph ^= 1; } }
           }
+          tc_commit(&mma_done[i]);
+          if (p.trace && blockIdx.x == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 1] = clock64();
         }
-        if (lane == 0) tc_commit(&mma_done[i]);
-        if (p.trace && blockIdx.x == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 1] = clock64();
-        __syncwarp();
       }
     }
   } else if (warp >= CH_HID_WARP0 && warp < CH_OUT_WARP0) {
@@ -374,7 +422,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     const int quad = warp & 3;
     const int half = ew >> 2;
     EpiStage es;
-    es.buf[0] = es.buf[1] = epi_tiles + ew * CH_EPI_TILE;
+    es.buf[0] = es.buf[1] = hid_tiles + ew * CH_EPI_TILE;
     es.aux_bar[0] = es.aux_bar[1] = nullptr; es.aux_phase[0] = es.aux_phase[1] = 0; es.uses = 0;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x, ++it) {
@@ -405,7 +453,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     const int quad = warp & 3;
     const int half = ew >> 2;
     EpiStage es;
-    es.buf[0] = epi_tiles + CH_EPI_WARPS * CH_EPI_TILE + ew * 2 * CH_EPI_TILE; es.buf[1] = es.buf[0] + CH_EPI_TILE;
+    es.buf[0] = out_tiles + ew * 2 * CH_EPI_TILE; es.buf[1] = es.buf[0] + CH_EPI_TILE;
     es.aux_bar[0] = &aux_bar[ew * 2]; es.aux_bar[1] = &aux_bar[ew * 2 + 1];
     es.aux_phase[0] = es.aux_phase[1] = 0; es.uses = 0;
     float loss_acc = 0.f;
@@ -414,6 +462,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     const int lchunks = lo.n_chunks * lo.n_chunk / 32;
     const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)lo.d_col;
     const uint32_t lbias = smem_u32(bias_s + lo.bias_off);
+    const uint64_t pol_stream = l2_policy_evict_first();
     uint32_t it = 0;
     for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x, ++it) {
       const uint32_t par = it & 1;
@@ -424,7 +473,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
         if (lane == 0) {
           bulk_wait_read<1>();          // the store that last used this buffer is done reading it
           mbar_expect_tx(es.aux_bar[b], CH_EPI_TILE);
-          tma_load_2d(&p.tmT, es.aux_bar[b], es.buf[b], half * 32, row0);
+          tma_load_2d_hint(&p.tmT, es.aux_bar[b], es.buf[b], half * 32, row0, pol_stream);
         }
         __syncwarp();
       }
@@ -441,7 +490,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
           if (lane == 0) {
             bulk_wait_read<0>();
             mbar_expect_tx(es.aux_bar[b ^ 1], CH_EPI_TILE);
-            tma_load_2d(&p.tmT, es.aux_bar[b ^ 1], es.buf[b ^ 1], nxt * 32, row0);
+            tma_load_2d_hint(&p.tmT, es.aux_bar[b ^ 1], es.buf[b ^ 1], nxt * 32, row0, pol_stream);
           }
           __syncwarp();
         } else if (!has_aux) {
@@ -473,7 +522,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) { tma_store_2d(&p.tmO[last], tile_p, ch * 32, row0); bulk_commit(); }
+        if (lane == 0) { tma_store_2d_hint(&p.tmO[last], tile_p, ch * 32, row0, pol_stream); bulk_commit(); }
         es.uses++;
       }
       tc_fence_before();

@@ -1,7 +1,7 @@
 // Whole-network tcgen05 kernel for the small-width MMAE configs (north star: "a persistent whole-network
 // kernel ... streams batches from HBM").  One launch runs a CHAIN of dense layers over 128-row tiles:
 //
-//   op 0     A = X tile streamed from HBM by TMA (k-chunks of 32 through a 4-deep ring, so the rows of the
+//   op 0     A = X tile streamed from HBM by TMA (k-chunks of 32 through a 4- to 6-deep ring, so the rows of the
 //            NEXT tile are already in flight while this tile computes), B = W_0 (K-major) k-chunks -> TMEM
 //   op i>0   A = the activated output of op i-1, which never leaves the SM: the epilogue of op i-1 reads
 //            its accumulator with tcgen05.ld (one thread = one row, 32 columns), applies bias + activation
@@ -36,15 +36,18 @@ constexpr int CH_THREADS = 640;
 constexpr int CH_HID_WARP0 = 4;
 constexpr int CH_OUT_WARP0 = 12;
 constexpr int CH_EPI_WARPS = 8;                  // per group
-constexpr int CH_XSTAGES = 4;
+constexpr int CH_MAX_XSTAGES = 8;
 constexpr int CH_XBYTES = TC_BM * TC_BK * 4;     // 16 KB: [128 rows][32 k]
-constexpr int CH_WRING_BYTES = 60 * 1024;        // weight k-chunks: [n_chunk n][32 k], slot size chosen per launch
+// X ring + W ring (+ the hidden warps' staging tiles when saved activations are wanted) share one pool; the split is
+// chosen per launch (weight k-chunks: [n_chunk n][32 k] slots; X k-chunks: 16 KB slots)
+constexpr int CH_POOL_BYTES = 156 * 1024;
 constexpr int CH_MAX_WSTAGES = 8;
 constexpr int CH_EPI_TILE = 32 * 32 * 4;         // 4 KB: [32 rows][32 cols], 128B swizzle
-constexpr int CH_EPI_BYTES = CH_EPI_WARPS * 3 * CH_EPI_TILE;   // one tile per hidden warp, two per output warp
+constexpr int CH_HID_BYTES = CH_EPI_WARPS * CH_EPI_TILE;       // one staging tile per hidden warp (inside the pool)
+constexpr int CH_OUT_BYTES = CH_EPI_WARPS * 2 * CH_EPI_TILE;   // two per output warp
 constexpr int CH_BIAS_FLOATS = 1024;
 constexpr int CH_BAR_BYTES = 1024;
-constexpr int CH_SMEM = CH_XSTAGES * CH_XBYTES + CH_WRING_BYTES + CH_EPI_BYTES + CH_BIAS_FLOATS * 4 + CH_BAR_BYTES + 1024;
+constexpr int CH_SMEM = CH_POOL_BYTES + CH_OUT_BYTES + CH_BIAS_FLOATS * 4 + CH_BAR_BYTES + 1024;
 constexpr int CH_TMEM_COLS = 512;
 static_assert(CH_SMEM <= 232448, "chain kernel shared memory exceeds the 227 KB per-CTA limit");
 
@@ -69,7 +72,7 @@ struct ChainParams {
   CUtensorMap tmT;                 // loss target of the last op
   ChainOp op[CH_MAX_OPS];
   int nops;
-  int w_slot_bytes, w_stages;
+  int w_slot_bytes, w_stages, x_stages, hid_tiles;
   int64_t M;
   int m_tiles;
   unsigned stagger_ns; // per-CTA start offset step: CTAs that all start together also all load / compute / store together,
@@ -153,8 +156,15 @@ inline bool chain_build(ChainParams& p, const float* X, int64_t M, int64_t ldx, 
   if (last.ep.fill_bits && (last.N > 512 || !last.ep.target || last.ep.mode != EPI_LOSS_PRED)) return false;
   if (last.ep.target && !make_tmap_io(&p.tmT, last.ep.target, M, last.N, last.ep.ldt)) return false;
   p.w_slot_bytes = ch_round_up(max_chunk * TC_BK * 4, 1024);
-  p.w_stages = std::min(CH_MAX_WSTAGES, CH_WRING_BYTES / p.w_slot_bytes);
-  if (p.w_stages < 2) return false;
+  p.hid_tiles = 0;
+  for (int i = 0; i + 1 < n; ++i) if (layers[i].out) p.hid_tiles = 1;
+  // pool split: 3 weight slots (L2 latency), the rest to X so that the next tile's rows stream in during this tile
+  const int pool = CH_POOL_BYTES - (p.hid_tiles ? CH_HID_BYTES : 0);
+  static const int env_ws = getenv("MMAE_CHAIN_WS") ? atoi(getenv("MMAE_CHAIN_WS")) : 3;
+  p.w_stages = std::min(CH_MAX_WSTAGES, std::max(2, env_ws));
+  while (p.w_stages > 2 && pool - p.w_stages * p.w_slot_bytes < 2 * CH_XBYTES) --p.w_stages;
+  p.x_stages = std::min(CH_MAX_XSTAGES, (pool - p.w_stages * p.w_slot_bytes) / CH_XBYTES);
+  if (p.w_stages < 2 || p.x_stages < 2) return false;
   return true;
 }
 

@@ -515,6 +515,7 @@ struct mmae_engine {
     int64_t B; bool noise; float keep; bool train_recon;   // train_recon: last layer emits delta_L
     bool decoder; bool headp; float* recon_out;
     float* fill_out = nullptr;     // whole-network kernel: write the filled matrix (A15) instead of decoded_X
+    bool need_mu = true;           // the embedding is wanted in global memory (it is not for plain predict / fill-in)
   };
 
   int begin_step(int64_t B, bool noise) {
@@ -627,7 +628,7 @@ struct mmae_engine {
       if (!l.Wkm) return 0;
       l.ep = epi(EPI_BIAS_ACT); l.ep.bias = pvar(bn);
       if (!last) { l.ep.act = cfg.activation; if (o.keep < 1.f) set_dropout(l.ep, o.keep, (uint32_t)i, dout); l.out = save ? ea[i] : nullptr; }
-      else { l.ep.act = MMAE_ACT_LINEAR; l.out = mu; }
+      else { l.ep.act = MMAE_ACT_LINEAR; l.out = (save || o.need_mu) ? mu : nullptr; }
       l.ldo = dout;
       ls.push_back(l); flops += 2.0 * din * dout;
     }
@@ -1221,6 +1222,7 @@ int mmae_forward(mmae_engine* e, const float* X_dev, const float* target_dev, co
   o.target = (want & MMAE_WANT_LOSS) ? (target_dev ? target_dev : X_dev) : nullptr;
   o.labels = labels_dev; o.train_recon = false; o.decoder = need_dec; o.headp = need_head;
   o.recon_out = (out && (want & MMAE_WANT_RECON)) ? out->recon : nullptr;
+  o.need_mu = need_head || (want & MMAE_WANT_EMBEDDING) != 0;
   e->fill_fused = false;
   const bool want_fill = (want & MMAE_WANT_FILLED) && out && out->filled;
   if (want_fill) {       // missing-block detection (data_funcs.py:366-381) runs first so the select can fuse into the last epilogue
