@@ -128,9 +128,9 @@ inline int64_t gemm_simt_num_ctas(int64_t M, int64_t N) {
 // Split count for a CUDA-core wgrad whose tile grid would leave most SMs idle (K = batch is the long dimension).
 inline int simt_pick_splits(int64_t M, int64_t N, int64_t K, int num_sms) {
   const int64_t tiles = gemm_simt_num_ctas(M, N);
-  if (tiles >= num_sms || K < 4096) return 1;
+  if (tiles >= num_sms || K < 512) return 1;
   int64_t s = (2 * num_sms + tiles - 1) / tiles;
-  const int64_t max_s = K / 1024;
+  const int64_t max_s = K / 128;        // >= 8 k-iterations per slice
   if (s > max_s) s = max_s;
   if (s > 64) s = 64;
   return (int)(s < 1 ? 1 : s);

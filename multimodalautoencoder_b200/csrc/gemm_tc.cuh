@@ -133,12 +133,12 @@ inline TcPlan tc_plan(const GemmArgs& g, int num_sms, int max_splits) {
   int64_t tiles = (int64_t)pl.m_blocks * pl.n_blocks;
   int64_t kblocks = (g.K + TC_BK - 1) / TC_BK;
   // split-K (wgrad only): pick the split count that best fills whole waves of the persistent grid, keeping at
-  // least 32 k-blocks per split and preferring fewer splits when the gain is below 3 % (slices cost HBM traffic)
+  // least 32 k-blocks per split (8 while the grid is still below one wave) and preferring fewer splits when the gain is below 3 % (slices cost HBM traffic)
   int splits = 1;
   if (max_splits > 1) {
     double best = 0.0;
     for (int s = 1; s <= max_splits; ++s) {
-      if (s > 1 && kblocks / s < 32) break;
+      if (s > 1 && kblocks / s < (tiles * s <= num_sms ? 8 : 32)) break;    // small grids: shorter slices beat idle SMs
       const int64_t total = tiles * s;
       const int64_t waves = (total + num_sms - 1) / num_sms;
       const double eff = (double)total / (double)(waves * num_sms);

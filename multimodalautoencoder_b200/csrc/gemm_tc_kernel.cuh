@@ -27,6 +27,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!done);
 }
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_saddr, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar_saddr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tc_commit_addr(uint32_t bar_saddr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_saddr) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -293,41 +306,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN, A_MN, B_MN);
-    int stage = 0; uint32_t phase = 0;
-    int64_t it = 0;
-    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      int mb, nb, sp; decode(t, mb, nb, sp);
-      const int64_t kb0 = (int64_t)sp * p.k_per_split;
-      const int64_t kend = min(p.K, kb0 + p.k_per_split);
-      const int as = (int)(it & 1); const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-      mbar_wait(&tempty_bar[as], aphase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-      uint32_t accumulate = 0;
-      for (int64_t k = kb0; k < kend; k += TC_BK) {
-        mbar_wait(&full_bar[stage], phase);
+    // One lane runs the loop; its serial instruction stream shares an issue port with two epilogue warps, so the
+    // per-k-block work is kept to waits + 4 MMAs + 1 commit: descriptors come from a precomputed base plus the
+    // stage address, all tile bookkeeping is done once per tile.
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN, A_MN, B_MN);
+      const uint64_t a_hi = !A_MN ? make_smem_desc(0, 16, 1024) : make_smem_desc(0, 4096, 512, 1);
+      const uint64_t b_hi = !B_MN ? make_smem_desc(0, 16, 1024) : make_smem_desc(0, 4096, 512, 1);
+      constexpr uint32_t a_step = !A_MN ? (32 >> 4) : (1024 >> 4);     // descriptor address units (16 B) per UMMA_K
+      constexpr uint32_t b_step = !B_MN ? (32 >> 4) : (1024 >> 4);
+      const uint32_t smem_s = smem_u32(smem);
+      const uint32_t full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar);
+      int stage = 0; uint32_t phase = 0;
+      int64_t it = 0;
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        int mb, nb, sp; decode(t, mb, nb, sp);
+        const int64_t kb0 = (int64_t)sp * p.k_per_split;
+        const int64_t kend = min(p.K, kb0 + p.k_per_split);
+        const int nkb = (int)((kend - kb0 + TC_BK - 1) / TC_BK);
+        const int as = (int)(it & 1); const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
-#pragma unroll
-          for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
-            // K-major: rows of 128 B, 8-row groups 1024 B apart; advance 32 B per UMMA_K inside the swizzle row.
-            // MN-major (SW128, 32B atoms): atoms [4 k][32 mn] of 512 B; MN chunks 4096 B apart (LBO), k groups
-            // 512 B apart (SBO); one UMMA_K = 8 spans two k groups = 1024 B.
-            uint64_t adesc = !A_MN ? make_smem_desc(sa + kk * 32, 16, 1024) : make_smem_desc(sa + kk * 1024, 4096, 512, 1);
-            uint64_t bdesc = !B_MN ? make_smem_desc(sb + kk * 32, 16, 1024) : make_smem_desc(sb + kk * 1024, 4096, 512, 1);
-            tc_mma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
-            accumulate = 1;
-          }
-          tc_commit(&empty_bar[stage]);              // smem stage reusable once these MMAs retire
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_addr(full_s + stage * 8u, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_s + stage * Cfg::kStageBytes;
+          const uint64_t adesc = a_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+          const uint64_t bdesc = b_hi | (uint64_t)(((sa + Cfg::kABytes) >> 4) & 0x3FFF);
+          tc_mma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+          tc_mma_tf32(tmem_d, adesc + a_step, bdesc + b_step, idesc, 1);
+          tc_mma_tf32(tmem_d, adesc + 2 * a_step, bdesc + 2 * b_step, idesc, 1);
+          tc_mma_tf32(tmem_d, adesc + 3 * a_step, bdesc + 3 * b_step, idesc, 1);
+          accumulate = 1;
+          tc_commit_addr(empty_s + stage * 8u);          // smem stage reusable once these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        tc_commit(&tfull_bar[as]);                       // accumulator complete
       }
-      if (lane == 0) tc_commit(&tfull_bar[as]);       // accumulator complete
-      __syncwarp();
     }
   } else {
     // ===================== epilogue warps (8): quadrant = warp % 4, two warps per quadrant =====================
