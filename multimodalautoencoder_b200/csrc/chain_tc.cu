@@ -273,9 +273,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
   uint64_t* wempty = wfull + CH_MAX_WSTAGES;            // [CH_MAX_WSTAGES]
   uint64_t* mma_done = wempty + CH_MAX_WSTAGES;         // [CH_MAX_OPS]      accumulator of op i complete
   uint64_t* chunk_done = mma_done + CH_MAX_OPS;         // [CH_MAX_OPS][CH_MAX_CHUNKS]  32 activated columns back in TMEM
-  uint64_t* last_done = chunk_done + CH_MAX_OPS * CH_MAX_CHUNKS;   // [1]    final op's accumulator drained
+  uint64_t* last_done = chunk_done + (CH_MAX_OPS - 1) * CH_MAX_CHUNKS;   // [1]    final op's accumulator drained (non-final ops <= 7)
   uint64_t* aux_bar = last_done + 1;                    // [CH_EPI_WARPS][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + CH_EPI_WARPS * 2);
+  uint64_t* miss_ready = aux_bar + CH_EPI_WARPS * 2;    // [2]  missing-block bits of a tile written (scan warp -> output warps)
+  uint64_t* miss_free = miss_ready + 2;                 // [2]  ... consumed (output warps -> scan warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(miss_free + 2);
   float* epi_red = reinterpret_cast<float*>(tmem_slot + 2);       // [CH_EPI_WARPS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -286,11 +288,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     for (int i = 0; i < p.nops; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB[i]) : "memory");
   }
   if (warp == 2 && lane == 0) {
-    for (int s = 0; s < CH_MAX_XSTAGES; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
+    for (int s = 0; s < CH_MAX_XSTAGES; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], p.scan_miss ? 1 + CH_EPI_WARPS : 1); }
     for (int s = 0; s < CH_MAX_WSTAGES; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int i = 0; i < CH_MAX_OPS; ++i) mbar_init(&mma_done[i], 1);
-    for (int i = 0; i < CH_MAX_OPS * CH_MAX_CHUNKS; ++i) mbar_init(&chunk_done[i], 4);     // one warp per lane quadrant
+    for (int i = 0; i < (CH_MAX_OPS - 1) * CH_MAX_CHUNKS; ++i) mbar_init(&chunk_done[i], 4);     // one warp per lane quadrant
     mbar_init(last_done, CH_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&miss_ready[i], CH_EPI_WARPS); mbar_init(&miss_free[i], CH_EPI_WARPS); }
     for (int i = 0; i < CH_EPI_WARPS * 2; ++i) mbar_init(&aux_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -305,6 +308,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     for (int c = threadIdx.x; c < w; c += CH_THREADS)
       bias_s[o.bias_off + c] = (o.ep.bias && c < o.N) ? __ldg(o.ep.bias + c) : 0.f;
   }
+  uint32_t* miss_s = reinterpret_cast<uint32_t*>(bias_s + CH_BIAS_FLOATS - 128 - 256);   // [2][128] missing-block bits per row
   uint8_t* lut = reinterpret_cast<uint8_t*>(bias_s + CH_BIAS_FLOATS - 128);          // column -> modality of the final op (fill-in)
   if (p.op[last].ep.fill_bits)
     for (int c = threadIdx.x; c < 512; c += CH_THREADS) lut[c] = c < p.op[last].N ? p.op[last].ep.fill_col_mod[c] : 0;
@@ -425,9 +429,51 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     es.buf[0] = es.buf[1] = hid_tiles + ew * CH_EPI_TILE;
     es.aux_bar[0] = es.aux_bar[1] = nullptr; es.aux_phase[0] = es.aux_phase[1] = 0; es.uses = 0;
     uint32_t it = 0;
+    int sxs = 0; uint32_t sxph = 0;
     for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x, ++it) {
       const uint32_t par = it & 1;
       const int64_t tile_row0 = (int64_t)t * TC_BM;
+      if (p.scan_miss) {
+        // fill-in: missing-block detection (sum == -width, data_funcs.py:366-381) from the X tile while it sits in the
+        // ring.  These warps are idle until the first layer's accumulator is complete; warp w owns rows [16w, 16w+16),
+        // a lane pair splits the 32 columns of a k-chunk.  Modalities are contiguous, increasing column ranges, so one
+        // running sum per row covers a block that spans several k-chunks.
+        const int K0 = p.op[0].K, x_stages = p.x_stages, num_mod = p.num_mod;
+        const uint32_t xring_s = smem_u32(xring);
+        const int r = ew * 16 + (lane & 15), hq = (lane >> 4) * 4;
+        float carry = 0.f; uint32_t bits = 0u; int m = 0;
+        for (int k0 = 0; k0 < K0; k0 += TC_BK) {
+          mbar_wait(&xfull[sxs], sxph);
+          const uint32_t base = xring_s + sxs * CH_XBYTES + r * 128;
+          const int kend = k0 + TC_BK;
+          float4 f[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) f[q] = lds128(base + (((hq + q) ^ (r & 7)) << 4));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&xempty[sxs]);          // with the MMA commit: 1 + 8 arrivals free the stage
+          if (++sxs == x_stages) { sxs = 0; sxph ^= 1; }
+          while (m < num_mod) {
+            const int s = __ldg(p.starts + m), e1 = __ldg(p.starts + m + 1);
+            if (s >= kend) break;
+            float part = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int c = k0 + (hq + q) * 4;
+              part += (c >= s && c < e1) ? f[q].x : 0.f;
+              part += (c + 1 >= s && c + 1 < e1) ? f[q].y : 0.f;
+              part += (c + 2 >= s && c + 2 < e1) ? f[q].z : 0.f;
+              part += (c + 3 >= s && c + 3 < e1) ? f[q].w : 0.f;
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 16);
+            if (e1 <= kend) { if (carry + part == -(float)(e1 - s)) bits |= 1u << m; carry = 0.f; ++m; }
+            else { carry += part; break; }
+          }
+        }
+        if (it >= 2) mbar_wait(&miss_free[it & 1], ((it >> 1) - 1) & 1);      // the tile that last used this slot is drained
+        if (lane < 16) miss_s[(it & 1) * 128 + r] = bits;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&miss_ready[it & 1]);
+      }
       for (int i = 0; i < last; ++i) {
         const ChainOp& o = p.op[i];
         mbar_wait(&mma_done[i], par);
@@ -481,7 +527,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
       tc_fence_after();
       if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + last) * 4 + 2] = clock64();
       const bool row_valid = (int64_t)row0 + lane < p.M;
-      const uint32_t miss = (lo.ep.fill_bits && row_valid) ? __ldg(lo.ep.fill_bits + row0 + lane) : 0u;
+      uint32_t miss = 0u;
+      if (p.scan_miss) { mbar_wait(&miss_ready[it & 1], (it >> 1) & 1); miss = miss_s[(it & 1) * 128 + quad * 32 + lane]; }
+      else if (lo.ep.fill_bits && row_valid) miss = __ldg(lo.ep.fill_bits + row0 + lane);
       for (int ch = half; ch < lchunks; ch += 2) {
         if (ch * 32 >= lo.N) break;                                   // padding columns only
         const int b = es.uses & 1;
@@ -528,7 +576,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + last) * 4 + 3] = clock64();
-      if (lane == 0) mbar_arrive(last_done);
+      if (lane == 0) { mbar_arrive(last_done); if (p.scan_miss) mbar_arrive(&miss_free[it & 1]); }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every output tile has landed
     if (lo.ep.loss_partials) {

@@ -75,6 +75,9 @@ struct ChainParams {
   int w_slot_bytes, w_stages, x_stages, hid_tiles;
   int64_t M;
   int m_tiles;
+  // fill-in: detect the missing blocks of each row (sum == -width, data_funcs.py:366-381) from the X tile while it sits in
+  // the shared-memory ring, instead of a separate pass over X.  starts = modality start columns [num_mod + 1] (device).
+  int scan_miss, num_mod; const int32_t* starts;
   unsigned stagger_ns; // per-CTA start offset step: CTAs that all start together also all load / compute / store together,
                        // so HBM and L2 see bursts; offsetting them over one tile period smooths the demand (0 = off)
   int dbg;             // debug switches (MMAE_CHAIN_DBG): 1 = output epilogue skips its math
@@ -153,6 +156,7 @@ inline bool chain_build(ChainParams& p, const float* X, int64_t M, int64_t ldx, 
     if (l.out && !make_tmap_io(&p.tmO[i], l.out, M, l.N, l.ldo)) return false;
   }
   if (bias_off > CH_BIAS_FLOATS - 128) return false;      // the last 512 bytes hold the fill-in column -> modality table
+  if (last.ep.fill_bits && bias_off > CH_BIAS_FLOATS - 128 - 256) return false;      // 1 KB before the table: per-row missing-block bits
   if (last.ep.fill_bits && (last.N > 512 || !last.ep.target || last.ep.mode != EPI_LOSS_PRED)) return false;
   if (last.ep.target && !make_tmap_io(&p.tmT, last.ep.target, M, last.N, last.ep.ldt)) return false;
   p.w_slot_bytes = ch_round_up(max_chunk * TC_BK * 4, 1024);

@@ -663,6 +663,7 @@ struct mmae_engine {
     }
     ChainParams cp;
     if (!chain_build(cp, a, B, F, ls)) return 0;
+    if (o.fill_out && M <= 32) { cp.scan_miss = 1; cp.num_mod = M; cp.starts = d_starts; }
     const int grid = std::min(cp.m_tiles, num_sms);
     static const bool want_trace = getenv("MMAE_CHAIN_TRACE") != nullptr;
     static const int chain_dbg = getenv("MMAE_CHAIN_DBG") ? atoi(getenv("MMAE_CHAIN_DBG")) : 0;
@@ -1225,11 +1226,13 @@ int mmae_forward(mmae_engine* e, const float* X_dev, const float* target_dev, co
   o.need_mu = need_head || (want & MMAE_WANT_EMBEDDING) != 0;
   e->fill_fused = false;
   const bool want_fill = (want & MMAE_WANT_FILLED) && out && out->filled;
-  if (want_fill) {       // missing-block detection (data_funcs.py:366-381) runs first so the select can fuse into the last epilogue
+  const bool fuse_fill = want_fill && !(want & MMAE_WANT_RECON) && !use_noise;
+  if (fuse_fill) o.fill_out = out->filled;      // detection + select both inside the whole-network kernel when it applies
+  if (want_fill && !fuse_fill) {       // missing-block detection (data_funcs.py:366-381) as its own pass
     const int wpb = 8;
-    missing_bits_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(X_dev, batch, e->F, e->d_starts, e->M, e->miss_bits);
+    const unsigned mb_grid = (unsigned)std::min<int64_t>((batch + wpb - 1) / wpb, (int64_t)e->num_sms * 8);
+    missing_bits_kernel<<<mb_grid, wpb * 32, 0, e->stream>>>(X_dev, batch, e->F, e->d_starts, e->M, e->miss_bits);
     ++e->launches;
-    if (!(want & MMAE_WANT_RECON) && !use_noise) o.fill_out = out->filled;
   }
   r = e->forward(o); if (r) return r;
   cudaError_t ce = cudaSuccess;
@@ -1238,6 +1241,12 @@ int mmae_forward(mmae_engine* e, const float* X_dev, const float* target_dev, co
   if (ce != cudaSuccess) return e->cuda_fail(ce, "embedding copy");
   if (want_fill && !e->fill_fused) {
     const float* rec = o.recon_out ? o.recon_out : e->out;
+    if (fuse_fill) {        // the whole-network kernel did not apply: detect the missing blocks now
+      const int wpb = 8;
+      const unsigned mb_grid = (unsigned)std::min<int64_t>((batch + wpb - 1) / wpb, (int64_t)e->num_sms * 8);
+      missing_bits_kernel<<<mb_grid, wpb * 32, 0, e->stream>>>(X_dev, batch, e->F, e->d_starts, e->M, e->miss_bits);
+      ++e->launches;
+    }
     fill_select_kernel<<<e->grid_for(batch * e->F, 256), 256, 0, e->stream>>>(X_dev, rec, e->miss_bits, e->d_col_mod, out->filled, batch, e->F);
     ++e->launches;
     ce = cudaGetLastError();

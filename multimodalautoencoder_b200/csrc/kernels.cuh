@@ -331,31 +331,33 @@ __global__ void missing_bits_kernel(const float* __restrict__ X, int64_t batch, 
                                     const int32_t* __restrict__ starts, int num_mod, uint32_t* __restrict__ miss) {
   // one warp per row; 256 columns per pass, all 8 loads of a lane in flight before any reduction.  Modalities are
   // contiguous column ranges in increasing order, so one running carry covers a block that spans passes.
-  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  int lane = threadIdx.x & 31;
-  if (row >= batch) return;
-  const float* x = X + row * (int64_t)num_feats;
-  uint32_t bits = 0u;
-  int m = 0;
-  float carry = 0.f;
-  for (int p0 = 0; p0 < num_feats && m < num_mod; p0 += 256) {
-    float v[8];
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  // persistent: a fixed grid of warps strides over the rows (10 M one-row blocks would be bound by block launch rate)
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < batch; row += nwarps) {
+    const float* x = X + row * (int64_t)num_feats;
+    uint32_t bits = 0u;
+    int m = 0;
+    float carry = 0.f;
+    for (int p0 = 0; p0 < num_feats && m < num_mod; p0 += 256) {
+      float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { const int c = p0 + e * 32 + lane; v[e] = c < num_feats ? __ldg(x + c) : 0.f; }
-    const int pend = min(num_feats, p0 + 256);
-    while (m < num_mod && starts[m] < pend) {
-      const int s = starts[m], e1 = starts[m + 1];
-      float part = 0.f;
+      for (int e = 0; e < 8; ++e) { const int c = p0 + e * 32 + lane; v[e] = c < num_feats ? __ldg(x + c) : 0.f; }
+      const int pend = min(num_feats, p0 + 256);
+      while (m < num_mod && starts[m] < pend) {
+        const int s = starts[m], e1 = starts[m + 1];
+        float part = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { const int c = p0 + e * 32 + lane; part += (c >= s && c < e1) ? v[e] : 0.f; }
-      part = warp_sum(part);
-      if (e1 <= pend) {
-        if (carry + part == -(float)(e1 - s)) bits |= 1u << m;
-        carry = 0.f; ++m;
-      } else { carry += part; break; }
+        for (int e = 0; e < 8; ++e) { const int c = p0 + e * 32 + lane; part += (c >= s && c < e1) ? v[e] : 0.f; }
+        part = warp_sum(part);
+        if (e1 <= pend) {
+          if (carry + part == -(float)(e1 - s)) bits |= 1u << m;
+          carry = 0.f; ++m;
+        } else { carry += part; break; }
+      }
     }
+    if (lane == 0) miss[row] = bits;
   }
-  if (lane == 0) miss[row] = bits;
 }
 __global__ void fill_select_kernel(const float* __restrict__ X, const float* __restrict__ recon,
                                    const uint32_t* __restrict__ miss, const uint8_t* __restrict__ col_mod,
