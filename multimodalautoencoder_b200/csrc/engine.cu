@@ -489,6 +489,11 @@ struct mmae_engine {
   int colsum(const float* D, int64_t rows, int n, int64_t ld, float* outp) {
     int splits = (int)std::max<int64_t>(1, std::min<int64_t>(64, rows / 256));
     dim3 grid((n + 31) / 32, splits), block(32, 8);
+    if (splits == 1) {       // small batches: one pass straight into the gradient (one launch instead of two)
+      colsum_partial_kernel<<<grid, block, 0, stream>>>(D, rows, n, ld, outp, 1);
+      CKL("colsum");
+      return 0;
+    }
     colsum_partial_kernel<<<grid, block, 0, stream>>>(D, rows, n, ld, colsum_ws, splits);
     CKL("colsum_partial");
     colsum_final_kernel<<<(n + 127) / 128, 128, 0, stream>>>(colsum_ws, n, splits, outp);
