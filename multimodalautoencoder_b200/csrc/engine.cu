@@ -449,11 +449,13 @@ struct mmae_engine {
         const float* wt = shadowT(B, k, n);
         if (wt) { g.B = wt; g.ldb = k; tb = true; }
       }
-      TcPlan pl = tc_plan(g, num_sms, allow_splitk && ep.mode == EPI_PLAIN ? 64 : 1);
+      const bool two_sm = tc2_eligible(ta, tb, g);       // 256 x 256 tiles on CTA pairs (cta_group::2)
+      const int max_s = allow_splitk && ep.mode == EPI_PLAIN ? 64 : 1;
+      TcPlan pl = two_sm ? tc2_plan(g, num_sms, max_s) : tc_plan(g, num_sms, max_s);
       if (pl.splits > 1) RET(ensure_splitk((int64_t)pl.splits * m * n));
       int pr = prof_begin(2.0 * (double)m * (double)n * (double)k);
       if (pr >= 0) { auto& R = prof_recs[pr]; R.m = m; R.n = n; R.k = k; R.ta = ta; R.tb = tb; R.splits = pl.splits; }
-      cudaError_t e = launch_gemm_tc(ta, tb, g, pl, splitk_ws, stream);
+      cudaError_t e = two_sm ? launch_gemm_tc2(ta, tb, g, pl, splitk_ws, stream) : launch_gemm_tc(ta, tb, g, pl, splitk_ws, stream);
       prof_end(pr);
       ++launches;
       if (e != cudaSuccess) return cuda_fail(e, "tcgen05 gemm launch");
@@ -1561,8 +1563,10 @@ int mmae_debug_gemm(int precision, int transA, int transB, int64_t M, int64_t N,
   if (precision == MMAE_PREC_TF32) {
     if (!tc_gemm_eligible(transA != 0, transB != 0, g)) return MMAE_ERR_INVALID;
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    TcPlan pl = tc_plan(g, sms, 1);
-    cudaError_t e = launch_gemm_tc(transA != 0, transB != 0, g, pl, nullptr, st);
+    const bool two_sm = tc2_eligible(transA != 0, transB != 0, g);
+    TcPlan pl = two_sm ? tc2_plan(g, sms, 1) : tc_plan(g, sms, 1);
+    cudaError_t e = two_sm ? launch_gemm_tc2(transA != 0, transB != 0, g, pl, nullptr, st)
+                           : launch_gemm_tc(transA != 0, transB != 0, g, pl, nullptr, st);
     return e == cudaSuccess ? 0 : MMAE_ERR_CUDA;
   }
   cudaError_t e = launch_gemm_simt(transA != 0, transB != 0, g, st);

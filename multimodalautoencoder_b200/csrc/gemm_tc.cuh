@@ -190,4 +190,66 @@ inline cudaError_t launch_gemm_tc(bool ta, bool tb, const GemmArgs& g, const TcP
   return tc_launch_64(a_mn, b_mn, p, pl.grid, st);
 }
 
+// ------------------------------------------------------------------ two-SM variant (gemm_tc2.cu): 256 x 256 tiles on CTA pairs
+cudaError_t tc2_launch(bool a_mn, bool b_mn, const TcParams& p, int grid, cudaStream_t st);
+
+inline bool tc2_eligible(bool ta, bool tb, const GemmArgs& g) {
+  static int on = -1;
+  if (on < 0) { const char* ev = getenv("MMAE_TC2"); on = (ev && ev[0] == '0') ? 0 : 1; }
+  if (!on || !tc_gemm_eligible(ta, tb, g)) return false;
+  if (g.M < 256 || g.N <= 128) return false;                 // narrower problems keep the one-SM tiles
+  if (ta && (g.M % 32)) return false;                        // MN-major operands go through the 3-D maps
+  if (!tb && (g.N % 32)) return false;
+  return true;
+}
+
+inline TcPlan tc2_plan(const GemmArgs& g, int num_sms, int max_splits) {
+  TcPlan pl;
+  const int pairs = num_sms / 2;
+  pl.bn = 256;
+  pl.m_blocks = (int)((g.M + 255) / 256);
+  pl.n_blocks = (int)((g.N + 255) / 256);
+  const int64_t tiles = (int64_t)pl.m_blocks * pl.n_blocks;
+  const int64_t kblocks = (g.K + TC_BK - 1) / TC_BK;
+  int splits = 1;
+  if (max_splits > 1) {
+    double best = 0.0;
+    for (int s = 1; s <= max_splits; ++s) {
+      if (s > 1 && kblocks / s < (tiles * s <= pairs ? 8 : 32)) break;
+      const int64_t total = tiles * s;
+      const int64_t waves = (total + pairs - 1) / pairs;
+      const double eff = (double)total / (double)(waves * pairs);
+      if (eff > best + 0.03) { best = eff; splits = s; }
+    }
+  }
+  const int64_t kb_per = (kblocks + splits - 1) / splits;
+  pl.k_per_split = kb_per * TC_BK;
+  pl.splits = (int)((kblocks + kb_per - 1) / kb_per);
+  const int64_t total = tiles * pl.splits;
+  pl.grid = 2 * (int)(total < pairs ? total : pairs);
+  return pl;
+}
+
+inline cudaError_t launch_gemm_tc2(bool ta, bool tb, const GemmArgs& g, const TcPlan& pl, float* splitk_ws, cudaStream_t st) {
+  TcParams p;
+  const bool a_mn = ta, b_mn = !tb;
+  bool ok = true;
+  p.a3d = a_mn ? 1 : 0; p.b3d = b_mn ? 1 : 0;
+  if (!a_mn) ok = ok && make_tmap(&p.tmA, g.A, g.M, g.K, g.lda, TC_BK, TC_BM);
+  else ok = ok && make_tmap_mn3d(&p.tmA, g.A, g.K, g.M, g.lda, TC_BK, TC_BM / 32);
+  if (!b_mn) ok = ok && make_tmap(&p.tmB, g.B, g.N, g.K, g.ldb, TC_BK, 128);            // each CTA of the pair stages half of the 256 columns
+  else ok = ok && make_tmap_mn3d(&p.tmB, g.B, g.K, g.N, g.ldb, TC_BK, 128 / 32);
+  if (!ok) return cudaErrorInvalidValue;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits; p.k_per_split = pl.k_per_split;
+  p.ep = g.ep;
+  if (pl.splits > 1) {
+    p.C = splitk_ws; p.ldc = g.N; p.split_stride = g.M * g.N;
+    p.ep.mode = EPI_PLAIN; p.ep.beta = 0.f; p.ep.loss_partials = nullptr;
+  } else {
+    p.C = g.C; p.ldc = g.ldc; p.split_stride = 0;
+  }
+  return tc2_launch(a_mn, b_mn, p, pl.grid, st);
+}
+
 }  // namespace mmae

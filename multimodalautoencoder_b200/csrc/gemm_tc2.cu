@@ -1,0 +1,250 @@
+// Two-SM tcgen05 GEMM (cta_group::2): a CTA pair (cluster of 2, same TPC) computes one 256 x 256 tile.
+//
+// Why: kind::tf32 operands are 4 bytes wide.  A single-SM 128 x 256 tile reads A (16 KB) + B (32 KB) per 32-wide
+// k-block from shared memory while the MMAs of that k-block take 256 clocks: 192 B/clk against the 128 B/clk an SM's
+// shared memory delivers (ncu: tensor pipe active 80 % at best).  With cta_group::2 each CTA stages its own 128 rows
+// of A and only HALF of B (128 of the 256 columns); the tensor cores of both SMs read both halves.  32 KB per
+// k-block per SM = 128 B/clk, and the smaller stage allows a 6-deep ring.
+//
+//   CTA rank r of the pair:  A rows [256*mb + 128*r, +128),  B columns [256*nb + 128*r, +128)
+//   TMA (cp.async.bulk.tensor ... cta_group::2): both CTAs' loads complete_tx on the LEADER's full barrier
+//   MMA: one lane of the leader CTA issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 8);
+//        tcgen05.commit ... multicast::cluster frees the stage / publishes the accumulator in BOTH CTAs
+//   TMEM: 2 accumulator stages x 256 columns in each CTA (its 128 rows); each CTA's 8 epilogue warps drain their
+//        own rows with the same fused epilogues as the one-SM kernel and arrive on the leader's "drained" barrier.
+#include <cooperative_groups.h>
+
+#include "gemm_tc_kernel.cuh"
+
+namespace mmae {
+
+constexpr int TC2_BN = 256;
+constexpr int TC2_BN_HALF = 128;
+constexpr int TC2_STAGES = 6;
+constexpr int TC2_ABYTES = TC_BM * TC_BK * 4;            // 16 KB
+constexpr int TC2_BBYTES = TC2_BN_HALF * TC_BK * 4;      // 16 KB
+constexpr int TC2_STAGE_BYTES = TC2_ABYTES + TC2_BBYTES;
+constexpr int TC2_EPI_BYTES = TC_EPI_WARPS * 32 * TC_STAGE_LD * 4;
+constexpr int TC2_SMEM = TC2_STAGES * TC2_STAGE_BYTES + TC2_EPI_BYTES + 1024 + 256;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;              // shared::cluster address of the same offset in the pair's leader CTA
+
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* tm, uint32_t leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(const CUtensorMap* tm, uint32_t leader_bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc2_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have retired
+__device__ __forceinline__ void tc2_commit_both(uint32_t bar_saddr) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar_saddr), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC2_STAGES * TC2_STAGE_BYTES);
+  uint64_t* full_bar = bars;                          // [TC2_STAGES]  (the leader's is the one that counts)
+  uint64_t* empty_bar = bars + TC2_STAGES;            // [TC2_STAGES]
+  uint64_t* tfull_bar = bars + 2 * TC2_STAGES;        // [2]
+  uint64_t* tempty_bar = bars + 2 * TC2_STAGES + 2;   // [2]  leader's: 16 arrivals (8 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC2_STAGES + 4);
+  float* epi_red = reinterpret_cast<float*>(tmem_slot + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int64_t tiles_mn = (int64_t)p.m_blocks * p.n_blocks;       // m_blocks counts 256-row blocks here
+  const int64_t num_tiles = tiles_mn * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {   // both CTAs of the pair allocate (same logical warp, same slot address)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();            // the peer's barriers exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int64_t t, int& mb, int& nb, int& sp) {
+    sp = (int)(t / tiles_mn);
+    int64_t r = t - (int64_t)sp * tiles_mn;
+    mb = (int)(r / p.n_blocks);
+    nb = (int)(r - (int64_t)mb * p.n_blocks);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane per CTA): own rows of A, own half of B =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t full_s = smem_u32(full_bar);
+      for (int64_t t = pair; t < num_tiles; t += num_pairs) {
+        int mb, nb, sp; decode(t, mb, nb, sp);
+        const int64_t kb0 = (int64_t)sp * p.k_per_split;
+        const int64_t kend = min(p.K, kb0 + p.k_per_split);
+        const int m0 = mb * 256 + (int)rank * TC_BM;
+        const int n0 = nb * TC2_BN + (int)rank * TC2_BN_HALF;
+        for (int64_t k = kb0; k < kend; k += TC_BK) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * TC2_STAGE_BYTES;
+          uint8_t* sb = sa + TC2_ABYTES;
+          const uint32_t lbar = (full_s + stage * 8u) & kPeerMask;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * TC2_STAGE_BYTES);      // both CTAs' bytes land on the leader's barrier
+          if (!A_MN) tma2_load_2d(&p.tmA, lbar, sa, (int)k, m0);                      // box {32 k, 128 m}
+          else tma2_load_3d(&p.tmA, lbar, sa, 0, (int)k, m0 / 32);                    // box {32 m, 32 k, 4 chunks}
+          if (!B_MN) tma2_load_2d(&p.tmB, lbar, sb, (int)k, n0);                      // box {32 k, 128 n}
+          else tma2_load_3d(&p.tmB, lbar, sb, 0, (int)k, n0 / 32);                    // box {32 n, 32 k, 4 chunks}
+          if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one lane of the leader CTA =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(TC2_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint64_t a_hi = !A_MN ? make_smem_desc(0, 16, 1024) : make_smem_desc(0, 4096, 512, 1);
+      const uint64_t b_hi = !B_MN ? make_smem_desc(0, 16, 1024) : make_smem_desc(0, 4096, 512, 1);
+      constexpr uint32_t a_step = !A_MN ? (32 >> 4) : (1024 >> 4);
+      constexpr uint32_t b_step = !B_MN ? (32 >> 4) : (1024 >> 4);
+      const uint32_t smem_s = smem_u32(smem);
+      const uint32_t full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar), tfull_s = smem_u32(tfull_bar);
+      int stage = 0; uint32_t phase = 0;
+      int64_t it = 0;
+      for (int64_t t = pair; t < num_tiles; t += num_pairs, ++it) {
+        int mb, nb, sp; decode(t, mb, nb, sp);
+        const int64_t kb0 = (int64_t)sp * p.k_per_split;
+        const int64_t kend = min(p.K, kb0 + p.k_per_split);
+        const int nkb = (int)((kend - kb0 + TC_BK - 1) / TC_BK);
+        const int as = (int)(it & 1); const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * TC2_BN);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_addr(full_s + stage * 8u, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_s + stage * TC2_STAGE_BYTES;
+          const uint64_t adesc = a_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+          const uint64_t bdesc = b_hi | (uint64_t)(((sa + TC2_ABYTES) >> 4) & 0x3FFF);
+          tc2_mma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+          tc2_mma_tf32(tmem_d, adesc + a_step, bdesc + b_step, idesc, 1);
+          tc2_mma_tf32(tmem_d, adesc + 2 * a_step, bdesc + 2 * b_step, idesc, 1);
+          tc2_mma_tf32(tmem_d, adesc + 3 * a_step, bdesc + 3 * b_step, idesc, 1);
+          accumulate = 1;
+          tc2_commit_both(empty_s + stage * 8u);        // both CTAs' producers may refill the stage
+          if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc2_commit_both(tfull_s + as * 8u);             // accumulator complete in both CTAs
+      }
+    }
+  } else {
+    // ===================== epilogue warps (8 per CTA): this CTA's 128 rows, all 256 columns =====================
+    const int quad = warp & 3;
+    const int half = (warp - TC_EPI_WARP0) >> 2;
+    float* stg = reinterpret_cast<float*>(smem + TC2_STAGES * TC2_STAGE_BYTES + 256) + (warp - TC_EPI_WARP0) * 32 * TC_STAGE_LD;
+    float loss_acc = 0.f;
+    int64_t ldaux; const float* auxp = epilogue_aux_ptr(p.ep, &ldaux);
+    int64_t it = 0;
+    for (int64_t t = pair; t < num_tiles; t += num_pairs, ++it) {
+      int mb, nb, sp; decode(t, mb, nb, sp);
+      const int as = (int)(it & 1); const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int64_t row0 = (int64_t)mb * 256 + (int64_t)rank * TC_BM + quad * 32;
+      float* cbase = p.C + (int64_t)sp * p.split_stride;
+#pragma unroll 1
+      for (int ch = half; ch < TC2_BN / 32; ch += 2) {
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TC2_BN + ch * 32), r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * TC_STAGE_LD + j] = __uint_as_float(r[j]);   // lane = row
+        __syncwarp();
+        const int64_t col = (int64_t)nb * TC2_BN + ch * 32 + lane;                          // lane = column
+        if (col < p.N && row0 < p.M) {
+          EpiRowCtx c;
+          c.cp = cbase + row0 * p.ldc + col;
+          c.ap = auxp ? auxp + row0 * ldaux + col : nullptr;
+          c.ldc = p.ldc; c.ldaux = ldaux; c.stg = stg + lane;
+          c.nrows = (int)min((int64_t)32, p.M - row0);
+          c.bias_v = p.ep.bias ? __ldg(p.ep.bias + col) : 0.f;
+          c.beta = p.ep.beta; c.grow0 = row0 + p.ep.row0; c.col = col;
+          c.colsum_out = p.ep.colsum_partials ? p.ep.colsum_partials + (row0 >> 5) * p.N + col : nullptr;
+          epi_dispatch(p.ep, c, loss_acc);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);     // 16 arrivals (both CTAs) free the accumulator stage
+    }
+    if (p.ep.loss_partials) {
+      float w = warp_sum(loss_acc);
+      if (lane == 0) epi_red[warp - TC_EPI_WARP0] = w;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == TC_EPI_WARP0 && lane == 0) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < TC_EPI_WARPS; ++i) sacc += epi_red[i];
+        p.ep.loss_partials[blockIdx.x] = sacc;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();            // nobody frees TMEM / exits while the pair still works on it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+template <bool A_MN, bool B_MN>
+static cudaError_t tc2_launch_inst(const TcParams& p, int grid, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = gemm_tc2_kernel<A_MN, B_MN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<grid, TC_THREADS, TC2_SMEM, st>>>(p);      // cluster shape comes from __cluster_dims__
+  return cudaGetLastError();
+}
+
+cudaError_t tc2_launch(bool a_mn, bool b_mn, const TcParams& p, int grid, cudaStream_t st) {
+  if (!a_mn && !b_mn) return tc2_launch_inst<false, false>(p, grid, st);
+  if (!a_mn && b_mn) return tc2_launch_inst<false, true>(p, grid, st);
+  if (a_mn && !b_mn) return tc2_launch_inst<true, false>(p, grid, st);
+  return tc2_launch_inst<true, true>(p, grid, st);
+}
+
+}  // namespace mmae
