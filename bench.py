@@ -327,7 +327,7 @@ def main():
         hx = [torch.rand((Be, F)).pin_memory() for _ in range(2)]
         hy = (torch.rand((Be, w['labels'])) < 0.5).float().pin_memory() if head else None
         hs = torch.zeros((args.steps + args.warmup + 1, 8), dtype=torch.float64).pin_memory()
-        hout = np.empty((Be, F), np.float32) if not train else None
+        hout = torch.empty((Be, F)).pin_memory() if not train else None
 
         def estep(i):
             eng.set_rng_step(2000 + i)
@@ -337,7 +337,7 @@ def main():
                     eng.cls_train_step_host(hx[i % 2], hy, gen_noise=True)
                 eng.read_scalars_async(hs[i])
             else:
-                eng.forward_host(hx[i % 2].numpy(), filled=True)
+                eng.forward_host(hx[i % 2].numpy(), filled=True, out={'filled': hout.numpy()})
 
         for i in range(min(args.warmup, 3)):
             estep(i)

@@ -360,6 +360,11 @@ struct mmae_engine {
     return 0;
   }
   int64_t cap_acts = 0, cap_host = 0;
+  // pipelined host inference (mmae_forward_host on large batches): per-slot device staging of the outputs
+  cudaStream_t d2h_stream = nullptr;
+  float* pipe_out[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [slot][recon, filled, embedding]
+  int64_t pipe_cap = 0;
+  cudaEvent_t pipe_ready[2] = {nullptr, nullptr}, pipe_free[2] = {nullptr, nullptr};
   int ensure_acts(int64_t B) {
     RET(ensure_cap(B));
     if (B <= cap_acts) return 0;
@@ -407,6 +412,12 @@ struct mmae_engine {
     for (auto& r : prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (gstream) cudaStreamDestroy(gstream);
+    if (d2h_stream) cudaStreamDestroy(d2h_stream);
+    for (int i = 0; i < 2; ++i) {
+      for (int j = 0; j < 3; ++j) if (pipe_out[i][j]) cudaFree(pipe_out[i][j]);
+      if (pipe_ready[i]) cudaEventDestroy(pipe_ready[i]);
+      if (pipe_free[i]) cudaEventDestroy(pipe_free[i]);
+    }
     if (comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(comm); comm = nullptr; }
     for (auto ev : comm_events) cudaEventDestroy(ev);
     if (comm_done) cudaEventDestroy(comm_done);
@@ -1318,7 +1329,7 @@ int cls_core(mmae_engine* e, const float* Xd, const float* Yd, int64_t batch, in
 }
 mmae_engine::GraphKey graph_key(mmae_engine* e, int kind, const void* X, const void* Y, const void* T, int64_t B, int noise, float keep) {
   mmae_engine::GraphKey k; memset(&k, 0, sizeof(k));
-  k.kind = kind; k.X = X; k.Y = Y; k.T = T; k.B = B; k.noise = noise; k.keep = keep; k.gb = e->global_batch; k.fr = e->first_row;
+  k.kind = kind; k.X = X; k.Y = Y; k.T = T; k.B = B; k.noise = noise | (e->eps_injected ? 2 : 0); k.keep = keep; k.gb = e->global_batch; k.fr = e->first_row;
   k.stream = (void*)e->stream;
   return k;
 }
@@ -1372,10 +1383,77 @@ int mmae_cls_train_step_host(mmae_engine* e, const float* X_host, const float* l
   return release_stage(e, t);
 }
 
+namespace {
+// predict() / fill-in over a large host matrix: rows travel in chunks through a three-stage pipeline -- H2D on the copy
+// stream, the forward pass on the engine's stream, D2H on a third stream -- so that with pinned host buffers the pass
+// runs at PCIe speed in both directions at once instead of copy, compute, copy back to back.
+constexpr int64_t kPipeChunk = 131072;
+int forward_host_pipelined(mmae_engine* e, const float* X_host, int64_t batch, float keep, uint32_t want, const mmae_outputs* oh) {
+  const int64_t chunk = kPipeChunk;
+  int r = e->ensure_host(chunk); if (r) return r;
+  cudaError_t ce = cudaSuccess;
+  if (!e->d2h_stream) {
+    ce = cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && ce == cudaSuccess; ++i) {
+      ce = cudaEventCreateWithFlags(&e->pipe_ready[i], cudaEventDisableTiming);
+      if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->pipe_free[i], cudaEventDisableTiming);
+    }
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "pipeline setup");
+  }
+  if (e->pipe_cap < chunk) {
+    for (int i = 0; i < 2; ++i) {
+      const int64_t widths[3] = {e->F, e->F, e->E};
+      for (int j = 0; j < 3; ++j) {
+        if (e->pipe_out[i][j]) { cudaFree(e->pipe_out[i][j]); e->pipe_out[i][j] = nullptr; }
+        ce = cudaMalloc(&e->pipe_out[i][j], (size_t)chunk * widths[j] * 4);
+        if (ce != cudaSuccess) return e->cuda_fail(ce, "pipeline staging");
+      }
+    }
+    e->pipe_cap = chunk;
+  }
+  int n = 0;
+  for (int64_t r0 = 0; r0 < batch; r0 += chunk, ++n) {
+    const int64_t rows = std::min(chunk, batch - r0);
+    const int t = n & 1;
+    // H2D of this chunk as soon as the compute that last read the slot is done
+    if ((ce = cudaStreamWaitEvent(e->copy_stream, e->xin_free[t], 0)) != cudaSuccess) return e->cuda_fail(ce, "pipe wait");
+    if ((ce = cudaMemcpyAsync(e->xin[t], X_host + r0 * e->F, (size_t)rows * e->F * 4, cudaMemcpyHostToDevice, e->copy_stream)) != cudaSuccess)
+      return e->cuda_fail(ce, "pipe H2D");
+    cudaEventRecord(e->xin_ready[t], e->copy_stream);
+    cudaStreamWaitEvent(e->stream, e->xin_ready[t], 0);
+    cudaStreamWaitEvent(e->stream, e->pipe_free[t], 0);        // the D2H that last read this slot's outputs is done
+    mmae_outputs od; memset(&od, 0, sizeof(od));
+    if (want & MMAE_WANT_RECON) od.recon = e->pipe_out[t][0];
+    if (want & MMAE_WANT_FILLED) od.filled = e->pipe_out[t][1];
+    if (want & MMAE_WANT_EMBEDDING) od.embedding = e->pipe_out[t][2];
+    r = mmae_forward(e, e->xin[t], nullptr, nullptr, rows, 0, keep, want, &od); if (r) return r;
+    cudaEventRecord(e->xin_free[t], e->stream);
+    cudaEventRecord(e->pipe_ready[t], e->stream);
+    cudaStreamWaitEvent(e->d2h_stream, e->pipe_ready[t], 0);
+    if ((want & MMAE_WANT_RECON) && oh->recon)
+      ce = cudaMemcpyAsync((float*)oh->recon + r0 * e->F, od.recon, (size_t)rows * e->F * 4, cudaMemcpyDeviceToHost, e->d2h_stream);
+    if (ce == cudaSuccess && (want & MMAE_WANT_FILLED) && oh->filled)
+      ce = cudaMemcpyAsync((float*)oh->filled + r0 * e->F, od.filled, (size_t)rows * e->F * 4, cudaMemcpyDeviceToHost, e->d2h_stream);
+    if (ce == cudaSuccess && (want & MMAE_WANT_EMBEDDING) && oh->embedding)
+      ce = cudaMemcpyAsync((float*)oh->embedding + r0 * e->E, od.embedding, (size_t)rows * e->E * 4, cudaMemcpyDeviceToHost, e->d2h_stream);
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "pipe D2H");
+    cudaEventRecord(e->pipe_free[t], e->d2h_stream);
+  }
+  ce = cudaStreamSynchronize(e->d2h_stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "pipelined forward");
+  return 0;
+}
+}  // namespace
+
 int mmae_forward_host(mmae_engine* e, const float* X_host, const float* target_host, const float* labels_host,
                       int64_t batch, int use_noise, float keep, uint32_t want, const mmae_outputs* oh) {
   ENTER(e);
   if (!X_host) return e->fail(MMAE_ERR_INVALID, "null X");
+  const uint32_t rowwise = MMAE_WANT_RECON | MMAE_WANT_FILLED | MMAE_WANT_EMBEDDING;
+  if (batch > kPipeChunk && oh && want != 0 && (want & ~rowwise) == 0 && !use_noise && !target_host && !labels_host &&
+      !e->cfg.variational)
+    return forward_host_pipelined(e, X_host, batch, keep, want, oh);
   int r = e->ensure_host(batch); if (r) return r;
   r = e->ensure_acts(batch); if (r) return r;      // output staging borrows the delta / noisy workspaces
   const int ycols = e->H ? (e->cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? e->C : 1) : 0;

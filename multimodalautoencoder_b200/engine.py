@@ -329,9 +329,12 @@ class Engine:
         return a.ctypes.data_as(C.c_void_p), a.shape[0]
 
     def forward_host(self, X_host, target_host=None, labels_host=None, noise=False, keep=1.0, recon=False,
-                     embedding=False, head=False, loss=False, filled=False, head_loss=False):
-        """predict()-style call: NumPy in, NumPy out, copies inside the C call."""
+                     embedding=False, head=False, loss=False, filled=False, head_loss=False, out=None):
+        """predict()-style call: NumPy in, NumPy out, copies inside the C call.  `out` may map 'recon' / 'filled' /
+        'embedding' to preallocated C-contiguous float32 arrays (e.g. views of pinned torch tensors): batches above
+        131 072 rows then stream through an H2D / compute / D2H pipeline at PCIe speed."""
         X = np.ascontiguousarray(X_host, np.float32)
+        out = out or {}
         B = X.shape[0]
         tgt = None if target_host is None else np.ascontiguousarray(target_host, np.float32)
         lab = None if labels_host is None else np.ascontiguousarray(labels_host, np.float32)
@@ -341,11 +344,12 @@ class Engine:
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         if recon:
             want |= capi.WANT_RECON
-            res['recon'] = np.empty((B, self.cfg.num_feats), np.float32)
+            res['recon'] = out.get('recon') if out.get('recon') is not None else np.empty((B, self.cfg.num_feats), np.float32)
             o.recon = res['recon'].ctypes.data
         if embedding:
             want |= capi.WANT_EMBEDDING
-            res['embedding'] = np.empty((B, self.cfg.layer_sizes[-1]), np.float32)
+            res['embedding'] = (out.get('embedding') if out.get('embedding') is not None
+                                else np.empty((B, self.cfg.layer_sizes[-1]), np.float32))
             o.embedding = res['embedding'].ctypes.data
         if head or head_loss:
             want |= capi.WANT_HEAD
@@ -358,7 +362,7 @@ class Engine:
             want |= capi.WANT_LOSS
         if filled:
             want |= capi.WANT_FILLED
-            res['filled'] = np.empty((B, self.cfg.num_feats), np.float32)
+            res['filled'] = out.get('filled') if out.get('filled') is not None else np.empty((B, self.cfg.num_feats), np.float32)
             o.filled = res['filled'].ctypes.data
         if head_loss:
             want |= capi.WANT_HEAD_LOSS

@@ -133,3 +133,22 @@ def test_chain_fused_fill_in(with_loss):
     if with_loss:
         assert abs(e.scalars()['recon_loss'] - c['recon_loss']) <= 1e-3 * c['recon_loss']
     e.close()
+
+
+def test_pipelined_host_inference_matches_single_call():
+    """forward_host above 131 072 rows streams chunks through H2D / compute / D2H; the result equals the device call."""
+    ocfg, ecfg = make_cfgs(precision='tf32', tie=False)
+    rng = np.random.default_rng(12)
+    P = O.init_params(ocfg, rng)
+    B = 131072 * 2 + 4321
+    X = rng.uniform(0, 1, (B, 320)).astype(np.float32)
+    X[rng.uniform(size=B) < 0.3, 200:220] = -1.0
+    e = _engine(ecfg, P, True)
+    want = e.forward(X, filled=True, recon=False)['filled'].cpu().numpy()
+    wr = e.forward(X, recon=True, embedding=True)
+    out = {'filled': np.empty((B, 320), np.float32)}
+    got = e.forward_host(X, filled=True, out=out)['filled']
+    assert got is out['filled'] and np.array_equal(got, want)
+    r2 = e.forward_host(X, recon=True, embedding=True)
+    assert np.array_equal(r2['recon'], wr['recon'].cpu().numpy()) and np.array_equal(r2['embedding'], wr['embedding'].cpu().numpy())
+    e.close()
