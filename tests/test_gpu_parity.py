@@ -369,3 +369,39 @@ def test_large_batch_wgrad_splitk(prec):
         ok, info = _grad_ok(e.get_gradient(k), g, tol)
         assert ok, (k, info)
     e.close()
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'tf32'])
+def test_loss_curve_over_1k_steps(prec):
+    """North-star tolerance: 1e-3 relative on the loss curve over 1k steps (and on the final reconstruction RMSE),
+    engine vs fp64 oracle from the same weights, batches and masks.  RMSE loss, lr 1e-3, batch 128, block-mask noise."""
+    ocfg, ecfg = make_cfgs(precision=prec, tie=False, loss='mean_squared', lam=0.0, lr=1e-3)
+    B, N = 128, 4096
+    rng, Xall = _data(ocfg, N, 31)
+    P = O.init_params(ocfg, rng)
+    e = _engine(ecfg, P)
+    st = O.AdamState()
+    thr = PH.categorical_thresholds(ocfg.noise_p)
+    worst = 0.0
+    Xd = torch.empty((B, 320), device='cuda')
+    for step in range(1000):
+        idx = PH.batch_indices(0, step, B, N)
+        X = Xall[idx]
+        zb, mb = PH.noise_descriptor(0, step, B, 320, 5, 16, True, thr, e.type_masks, 1)
+        noisy = O.noise_from_descriptor(ocfg, X, zb, mb)
+        c, _ = O.train_step(ocfg, P, st, noisy, X)
+        e.set_rng_step(step)
+        e.gen_noise(B)
+        Xd.copy_(torch.as_tensor(X.astype(np.float32)))          # same device buffer every step: graph replay
+        e.train_step(Xd, noise=True)
+        if step % 10 == 0 or step == 999:
+            got = e.scalars()['recon_loss']
+            worst = max(worst, abs(got - c['recon_loss']) / c['recon_loss'])
+    assert e.graph_replays > 900
+    assert worst <= 1e-3, worst
+    # final reconstruction RMSE on held-out rows
+    Xv = Xall[:512]
+    r = e.forward(Xv.astype(np.float32), recon=True, loss=True)
+    cv = O.forward(ocfg, P, Xv, Xv)
+    assert abs(e.scalars()['recon_loss'] - cv['recon_loss']) <= 1e-3 * cv['recon_loss']
+    e.close()
