@@ -83,6 +83,7 @@ PROTOTYPES = {
     'mmae_kernel_launches': (_L, [_P]),
     'mmae_chain_launches': (_L, [_P]),
     'mmae_graph_replays': (_L, [_P]),
+    'mmae_fused_noise_launches': (_L, [_P]),
     'mmae_set_profiling': (_I, [_P, _I]),
     'mmae_read_profile': (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_L)]),
     'mmae_read_scalars_async': (_I, [_P, _P, _I]),

@@ -443,6 +443,12 @@ struct mmae_engine {
   void mark_dirty(int64_t begin, int64_t end) {
     for (size_t i = 0; i < vars.size(); ++i) if (vars[i].off >= begin && vars[i].off < end) pt_dirty[i] = 1;
   }
+  int fuse_noise_mode = -1;      // per engine, read at the first use: MMAE_FUSE_NOISE=1 opts in (measured slower, see gemm_tc2.cu)
+  bool noise_fusion_on() {
+    if (fuse_noise_mode < 0) { const char* ev = getenv("MMAE_FUSE_NOISE"); fuse_noise_mode = (ev && ev[0] == '1') ? 1 : 0; }
+    return fuse_noise_mode == 1;
+  }
+  bool starts_aligned32() const { for (int v : starts) if (v & 31) return false; return true; }
   bool last_gemm_tc = false;
   bool d_fused = false;      // the current delta's column-sum partials are valid in colpart
 
@@ -452,15 +458,19 @@ struct mmae_engine {
            int64_t ldb, float* Cp, int64_t ldc, const NoiseView& nv, const Epilogue& ep, int64_t* n_partials,
            bool allow_splitk) {
     GemmArgs g; g.splits = 1; g.k_per_split = 0; g.M = m; g.N = n; g.K = k; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = Cp; g.ldc = ldc;
-    g.noise = nv; g.ep = ep;
+    g.noise = nv; g.ep = ep; g.noise_aligned32 = starts_aligned32() ? 1 : 0;
     last_gemm_tc = false;
-    if (cfg.precision == MMAE_PREC_TF32 && tc_gemm_eligible(ta, tb, g)) {
+    bool tbk = tb;      // forward GEMMs read the K-major shadow of the weight: decide two-SM eligibility with that operand
+    if (!tb && (k & 3) == 0 && nv.enabled) { if (shadowT(B, k, n)) tbk = true; }
+    if (cfg.precision == MMAE_PREC_TF32 && (tc_gemm_eligible(ta, tb, g) || (nv.enabled && tc2_eligible(ta, tbk, g)))) {
       last_gemm_tc = true;
       if (!tb && (k & 3) == 0) {      // y = x.W with W stored [K,N]: use its K-major shadow W^T [N,K] when W is a variable
         const float* wt = shadowT(B, k, n);
         if (wt) { g.B = wt; g.ldb = k; tb = true; }
       }
       const bool two_sm = tc2_eligible(ta, tb, g);       // 256 x 256 tiles on CTA pairs (cta_group::2)
+      if (nv.enabled && !two_sm) return fail(MMAE_ERR_STATE, "internal: noisy operand reached the one-SM tcgen05 GEMM");
+      if (nv.enabled) ++fused_noise_launches;
       const int max_s = allow_splitk && ep.mode == EPI_PLAIN ? 64 : 1;
       TcPlan pl = two_sm ? tc2_plan(g, num_sms, max_s) : tc_plan(g, num_sms, max_s);
       if (pl.splits > 1) RET(ensure_splitk((int64_t)pl.splits * m * n));
@@ -626,6 +636,7 @@ struct mmae_engine {
   // resident in TMEM.  Returns 1 when it ran, 0 when the configuration does not fit (caller runs the per-layer
   // GEMMs), or a (negative) error code.
   int64_t chain_launches = 0;
+  int64_t fused_noise_launches = 0;      // two-SM GEMM launches that applied the mask + noise to their A tile in shared memory
   int chain_mode = -1;
   bool fill_fused = false;       // the last forward wrote the filled matrix from the whole-network kernel
   int forward_chain(const FwdOpts& o, const float* a) {
@@ -722,7 +733,12 @@ struct mmae_engine {
     const float* a = o.X;
     NoiseView nv = noise_view(o.noise);
     if (o.noise || o.train_recon || o.labels) RET(ensure_acts(B));
-    if (o.noise && cfg.precision == MMAE_PREC_TF32 && B >= 32 && (F & 3) == 0) {
+    // Wide first layers can go through the two-SM GEMM variant that applies the mask + noise to the A tile in shared
+    // memory (forward and the layer's wgrad), so that no noisy copy of X is ever written.  Measured slower than one
+    // materialising pass on this ring depth (see gemm_tc2.cu), hence opt-in (MMAE_FUSE_NOISE=1); default: materialise.
+    const bool fuse_noise = o.noise && cfg.precision == MMAE_PREC_TF32 && noise_fusion_on() && B >= 256 && F >= 256 &&
+                            (F & 31) == 0 && layers[0] > 256 && (layers[0] & 3) == 0;
+    if (o.noise && cfg.precision == MMAE_PREC_TF32 && B >= 32 && (F & 3) == 0 && !fuse_noise) {
       // the tcgen05 family reads its operands through TMA: materialise noisy_X once (first GEMM + its wgrad)
       noise_apply_kernel<<<grid_for(B * F, 256), 256, 0, stream>>>(o.X, noisy, B, F, nv);
       CKL("noise_apply");
@@ -1579,6 +1595,7 @@ int mmae_set_shard(mmae_engine* e, int64_t global_batch, int64_t first_row) {
 int64_t mmae_kernel_launches(const mmae_engine* e) { return e ? e->launches : 0; }
 int64_t mmae_chain_launches(const mmae_engine* e) { return e ? e->chain_launches : 0; }
 int64_t mmae_graph_replays(const mmae_engine* e) { return e ? e->graph_replays : 0; }
+int64_t mmae_fused_noise_launches(const mmae_engine* e) { return e ? e->fused_noise_launches : 0; }
 
 int mmae_set_profiling(mmae_engine* e, int on) {
   ENTER(e);

@@ -51,6 +51,9 @@ struct TcParams {
   int64_t split_stride;         // elements between split-K slices of C (0 when splits == 1)
   int a3d, b3d;                 // MN-major operand loaded through a 3-D map (one TMA per stage)
   Epilogue ep;
+  NoiseView nz;                 // two-SM kernel only: block-mask + zero noise applied to the A tile in shared memory
+  int l2_ahead;                 // two-SM kernel: k-blocks of A prefetched into L2 ahead of the shared-memory ring (0 = off)
+  int nz_aligned;               // every modality boundary is a multiple of 32 columns (one modality per 32-column chunk)
 };
 
 // ------------------------------------------------------------------ host side
@@ -110,9 +113,9 @@ inline bool make_tmap_mn3d(CUtensorMap* tm, const float* base, int64_t k_rows, i
   return r == CUDA_SUCCESS;
 }
 
-inline bool tc_gemm_eligible(bool ta, bool tb, const GemmArgs& g) {
+inline bool tc_gemm_eligible(bool ta, bool tb, const GemmArgs& g, bool allow_noise = false) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (g.noise.enabled) return false;                 // the noisy operand is materialised first on this path
+  if (g.noise.enabled && !allow_noise) return false; // one-SM family: the noisy operand is materialised first
   if ((g.lda & 3) || (g.ldb & 3) || (g.ldc & 3)) return false;
   if (!al(g.A) || !al(g.B) || !al(g.C)) return false;
   if (g.M < 32 || g.N < 32 || g.K < 32 || (g.N & 3)) return false;   // smaller dims ride on TMA zero-fill; below 32 the CUDA-core family wins
@@ -191,13 +194,14 @@ inline cudaError_t launch_gemm_tc(bool ta, bool tb, const GemmArgs& g, const TcP
 }
 
 // ------------------------------------------------------------------ two-SM variant (gemm_tc2.cu): 256 x 256 tiles on CTA pairs
-cudaError_t tc2_launch(bool a_mn, bool b_mn, const TcParams& p, int grid, cudaStream_t st);
+cudaError_t tc2_launch(bool a_mn, bool b_mn, bool noise, const TcParams& p, int grid, cudaStream_t st);
 
 inline bool tc2_eligible(bool ta, bool tb, const GemmArgs& g) {
   static int on = -1;
   if (on < 0) { const char* ev = getenv("MMAE_TC2"); on = (ev && ev[0] == '0') ? 0 : 1; }
-  if (!on || !tc_gemm_eligible(ta, tb, g)) return false;
+  if (!on || !tc_gemm_eligible(ta, tb, g, true)) return false;
   if (g.M < 256 || g.N <= 128) return false;                 // narrower problems keep the one-SM tiles
+  if (g.noise.enabled && ta != !tb) return false;            // noise on A: forward (K-major A, K-major B) or its wgrad (both MN-major)
   if (ta && (g.M % 32)) return false;                        // MN-major operands go through the 3-D maps
   if (!tb && (g.N % 32)) return false;
   return true;
@@ -249,7 +253,10 @@ inline cudaError_t launch_gemm_tc2(bool ta, bool tb, const GemmArgs& g, const Tc
   } else {
     p.C = g.C; p.ldc = g.ldc; p.split_stride = 0;
   }
-  return tc2_launch(a_mn, b_mn, p, pl.grid, st);
+  p.nz = g.noise; p.nz_aligned = g.noise_aligned32;
+  static const int l2a = getenv("MMAE_TC2_L2AHEAD") ? atoi(getenv("MMAE_TC2_L2AHEAD")) : 0;
+  p.l2_ahead = l2a;
+  return tc2_launch(a_mn, b_mn, g.noise.enabled != 0, p, pl.grid, st);
 }
 
 }  // namespace mmae

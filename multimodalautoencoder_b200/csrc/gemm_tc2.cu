@@ -25,7 +25,11 @@ constexpr int TC2_ABYTES = TC_BM * TC_BK * 4;            // 16 KB
 constexpr int TC2_BBYTES = TC2_BN_HALF * TC_BK * 4;      // 16 KB
 constexpr int TC2_STAGE_BYTES = TC2_ABYTES + TC2_BBYTES;
 constexpr int TC2_EPI_BYTES = TC_EPI_WARPS * 32 * TC_STAGE_LD * 4;
-constexpr int TC2_SMEM = TC2_STAGES * TC2_STAGE_BYTES + TC2_EPI_BYTES + 1024 + 256;
+constexpr int TC2_BAR_BYTES = 512;
+constexpr int TC2_SMEM = TC2_STAGES * TC2_STAGE_BYTES + TC2_EPI_BYTES + 1024 + TC2_BAR_BYTES;
+static_assert(TC2_SMEM <= 232448, "two-SM GEMM shared memory exceeds the per-CTA limit");
+constexpr int TC2_THREADS_NOISE = TC_THREADS + 128;      // + 4 warps that apply the mask / noise to the A tile in shared memory
+constexpr int TC2_PATCH_WARP0 = TC_THREADS / 32;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;              // shared::cluster address of the same offset in the pair's leader CTA
 
 __device__ __forceinline__ void tma2_load_2d(const CUtensorMap* tm, uint32_t leader_bar, void* dst, int c0, int c1) {
@@ -37,6 +41,14 @@ __device__ __forceinline__ void tma2_load_3d(const CUtensorMap* tm, uint32_t lea
   asm volatile(
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// L2 prefetch of a tile that will be loaded a few k-blocks from now: the shared-memory ring is only 6 stages deep, so the
+// HBM latency of A (activations stream from DRAM; the weights stay in L2) is taken out of the stage's critical path.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tc2_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -53,12 +65,46 @@ __device__ __forceinline__ void tc2_commit_both(uint32_t bar_saddr) {
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_leader_release(uint32_t bar_saddr) {      // makes this CTA's shared-memory writes visible to the pair
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_saddr & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar_saddr, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar_saddr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
+// Block-mask + zero noise (multimodal_autoencoder.py:668-702) on 32 consecutive stored columns of one batch row that sit
+// in shared memory at byte offsets base + ((4*j) ^ sw), j = 0..31 (sw: the row's swizzle term).  Block mask wins (:695
+// after :683).  `feat0` = first feature column of the 32.
+__device__ __forceinline__ void patch_row32(const NoiseView& nz, int aligned, uint32_t base, uint32_t sw, uint32_t zb, uint32_t mbits, int feat0, int nfeat) {
+  if (aligned) {
+    if ((mbits >> __ldg(nz.col_mod + feat0)) & 1u) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sts32(base + ((uint32_t)(4 * j) ^ sw), nz.mask_with);
+    } else {
+      while (zb) { const int j = __ffs(zb) - 1; zb &= zb - 1; sts32(base + ((uint32_t)(4 * j) ^ sw), 0.f); }
+    }
+  } else {
+    for (int j = 0; j < 32 && feat0 + j < nfeat; ++j) {
+      if ((mbits >> __ldg(nz.col_mod + feat0 + j)) & 1u) sts32(base + ((uint32_t)(4 * j) ^ sw), nz.mask_with);
+      else if ((zb >> j) & 1u) sts32(base + ((uint32_t)(4 * j) ^ sw), 0.f);
+    }
+  }
+}
+
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
+template <bool A_MN, bool B_MN, bool NOISE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NOISE ? TC2_THREADS_NOISE : TC_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC2_STAGES * TC2_STAGE_BYTES);
@@ -66,7 +112,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) gemm_
   uint64_t* empty_bar = bars + TC2_STAGES;            // [TC2_STAGES]
   uint64_t* tfull_bar = bars + 2 * TC2_STAGES;        // [2]
   uint64_t* tempty_bar = bars + 2 * TC2_STAGES + 2;   // [2]  leader's: 16 arrivals (8 epilogue warps x 2 CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC2_STAGES + 4);
+  uint64_t* afull_bar = bars + 2 * TC2_STAGES + 4;    // [TC2_STAGES]  NOISE: this CTA's A tile has landed (local)
+  uint64_t* aok_bar = afull_bar + TC2_STAGES;         // [TC2_STAGES]  NOISE: both CTAs' A tiles are patched (leader's: one warp per CTA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aok_bar + TC2_STAGES);
   float* epi_red = reinterpret_cast<float*>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -83,6 +131,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) gemm_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * TC_EPI_WARPS); }
+    for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aok_bar[s], 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {   // both CTAs of the pair allocate (same logical warp, same slot address)
@@ -113,13 +162,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) gemm_
         const int m0 = mb * 256 + (int)rank * TC_BM;
         const int n0 = nb * TC2_BN + (int)rank * TC2_BN_HALF;
         for (int64_t k = kb0; k < kend; k += TC_BK) {
+          if (p.l2_ahead > 0) {
+            const int64_t kp = k + (int64_t)p.l2_ahead * TC_BK;
+            if (kp < kend) { if (!A_MN) tma_prefetch_2d(&p.tmA, (int)kp, m0); else tma_prefetch_3d(&p.tmA, 0, (int)kp, m0 / 32); }
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * TC2_STAGE_BYTES;
           uint8_t* sb = sa + TC2_ABYTES;
           const uint32_t lbar = (full_s + stage * 8u) & kPeerMask;
+          if (NOISE) {      // A lands on this CTA's own barrier: the patch warps touch it before the MMA may
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * TC2_BBYTES);
+            mbar_expect_tx(&afull_bar[stage], TC2_ABYTES);
+            if (!A_MN) tma_load_2d(&p.tmA, &afull_bar[stage], sa, (int)k, m0);
+            else tma_load_3d(&p.tmA, &afull_bar[stage], sa, 0, (int)k, m0 / 32);
+          } else {
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * TC2_STAGE_BYTES);      // both CTAs' bytes land on the leader's barrier
           if (!A_MN) tma2_load_2d(&p.tmA, lbar, sa, (int)k, m0);                      // box {32 k, 128 m}
           else tma2_load_3d(&p.tmA, lbar, sa, 0, (int)k, m0 / 32);                    // box {32 m, 32 k, 4 chunks}
+          }
           if (!B_MN) tma2_load_2d(&p.tmB, lbar, sb, (int)k, n0);                      // box {32 k, 128 n}
           else tma2_load_3d(&p.tmB, lbar, sb, 0, (int)k, n0 / 32);                    // box {32 n, 32 k, 4 chunks}
           if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
@@ -151,6 +211,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) gemm_
         uint32_t accumulate = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait_addr(full_s + stage * 8u, phase);
+          if (NOISE) mbar_wait_acquire_cluster(smem_u32(aok_bar) + stage * 8u, phase);
           tc_fence_after();
           const uint32_t sa = smem_s + stage * TC2_STAGE_BYTES;
           const uint64_t adesc = a_hi | (uint64_t)((sa >> 4) & 0x3FFF);
@@ -166,11 +227,76 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) gemm_
         tc2_commit_both(tfull_s + as * 8u);             // accumulator complete in both CTAs
       }
     }
-  } else {
+  } else if (NOISE && warp >= TC2_PATCH_WARP0) {
+    // ===================== patch warps (4 per CTA): mask + noise on the A tile, in shared memory =====================
+    // "fused modality-block mask plus noise in the A-operand load of the first encoder GEMM": TMA lands the clean rows,
+    // these warps overwrite the masked blocks with mask_with and the 5 % noise cells with 0, then hand the tile to the
+    // tensor cores.  One work item = 32 stored columns of one batch row (= one word of the zero bitmap); a stage has
+    // 128 items.  Making the patched tile visible to the pair (proxy fence + cluster-scope release) costs ~1 us, far
+    // more than the 512 clocks a stage lasts, so the four warps take the k-blocks round-robin -- four stages are in
+    // flight -- and each warp covers a whole stage (4 items per lane).
+    // MEASURED (wide step, same box): 11.14 ms with a materialised noisy X (noise_apply_kernel, 0.35 ms) against
+    // 13.85 ms with this path (12.16 ms with cta-scope signalling, which is not formally sufficient across the pair):
+    // the ring is 6 stages deep and HBM latency already uses most of that depth, so any latency added between "tile
+    // landed" and "tile usable" lowers the stage rate.  The engine therefore keeps materialisation as the default and
+    // this path behind MMAE_FUSE_NOISE=1 (parity-tested either way).
+    //   K-major A (forward): item t = tile row (batch row m0 + t), columns k..k+31.
+    //   MN-major A (wgrad): item t = (chunk t / 32, batch row k + t % 32), feature columns m0 + 32 (t / 32) .. +31.
+    const int pw = warp - TC2_PATCH_WARP0;
+    const uint32_t smem_s = smem_u32(smem);
+    const uint32_t aok_s = smem_u32(aok_bar);
+    const int64_t nrows = !A_MN ? p.M : p.K;
+    const int nfeat = !A_MN ? (int)p.K : (int)p.M;
+    uint32_t c = 0;                                   // k-blocks produced so far (all tiles): stage = c % STAGES
+    for (int64_t t = pair; t < num_tiles; t += num_pairs) {
+      int mb, nb, sp; decode(t, mb, nb, sp);
+      const int64_t kb0 = (int64_t)sp * p.k_per_split;
+      const int64_t kend = min(p.K, kb0 + p.k_per_split);
+      const int m0 = mb * 256 + (int)rank * TC_BM;
+      auto fetch = [&](int64_t k, uint32_t (&zb)[4], uint32_t (&mbits)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int tid = lane + 32 * j;
+          zb[j] = 0u; mbits[j] = 0u;
+          const int64_t brow = !A_MN ? (int64_t)m0 + tid : k + (tid & 31);
+          const int feat0 = !A_MN ? (int)k : m0 + (tid >> 5) * 32;
+          if (k < kend && brow < nrows && feat0 < nfeat) {
+            zb[j] = __ldg(p.nz.zero_bits + brow * p.nz.zw + (feat0 >> 5)); mbits[j] = __ldg(p.nz.mod_bits + brow);
+          }
+        }
+      };
+      uint32_t zq[4], mq[4], zn[4], mn[4];
+      // first k-block of this tile that is mine
+      int64_t k = kb0 + (int64_t)((pw - (int)(c & 3)) & 3) * TC_BK;
+      uint32_t cc = c + (uint32_t)((pw - (int)(c & 3)) & 3);
+      fetch(k, zq, mq);
+      for (; k < kend; k += 4 * TC_BK, cc += 4) {
+        fetch(k + 4 * TC_BK, zn, mn);
+        const uint32_t stage = cc % TC2_STAGES, phase = (cc / TC2_STAGES) & 1;
+        mbar_wait(&afull_bar[stage], phase);
+        const uint32_t sa = smem_s + stage * TC2_STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int tid = lane + 32 * j;
+          const int feat0 = !A_MN ? (int)k : m0 + (tid >> 5) * 32;
+          if (zq[j] | mq[j]) {
+            if (!A_MN) patch_row32(p.nz, p.nz_aligned, sa + tid * 128, (uint32_t)(tid & 7) << 4, zq[j], mq[j], feat0, nfeat);
+            else patch_row32(p.nz, p.nz_aligned, sa + (tid >> 5) * 4096 + (tid & 31) * 128, (uint32_t)(tid & 3) << 5, zq[j], mq[j], feat0, nfeat);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> visible to the tensor cores' reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader_release(aok_s + stage * 8u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { zq[j] = zn[j]; mq[j] = mn[j]; }
+      }
+      c += (uint32_t)((kend - kb0 + TC_BK - 1) / TC_BK);
+    }
+  } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_EPI_WARPS) {
     // ===================== epilogue warps (8 per CTA): this CTA's 128 rows, all 256 columns =====================
     const int quad = warp & 3;
     const int half = (warp - TC_EPI_WARP0) >> 2;
-    float* stg = reinterpret_cast<float*>(smem + TC2_STAGES * TC2_STAGE_BYTES + 256) + (warp - TC_EPI_WARP0) * 32 * TC_STAGE_LD;
+    float* stg = reinterpret_cast<float*>(smem + TC2_STAGES * TC2_STAGE_BYTES + TC2_BAR_BYTES) + (warp - TC_EPI_WARP0) * 32 * TC_STAGE_LD;
     float loss_acc = 0.f;
     int64_t ldaux; const float* auxp = epilogue_aux_ptr(p.ep, &ldaux);
     int64_t it = 0;
@@ -227,24 +353,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) gemm_
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool NOISE>
 static cudaError_t tc2_launch_inst(const TcParams& p, int grid, cudaStream_t st) {
   static bool configured = false;
-  auto kern = gemm_tc2_kernel<A_MN, B_MN>;
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, NOISE>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, TC_THREADS, TC2_SMEM, st>>>(p);      // cluster shape comes from __cluster_dims__
+  kern<<<grid, NOISE ? TC2_THREADS_NOISE : TC_THREADS, TC2_SMEM, st>>>(p);      // cluster shape comes from __cluster_dims__
   return cudaGetLastError();
 }
 
-cudaError_t tc2_launch(bool a_mn, bool b_mn, const TcParams& p, int grid, cudaStream_t st) {
-  if (!a_mn && !b_mn) return tc2_launch_inst<false, false>(p, grid, st);
-  if (!a_mn && b_mn) return tc2_launch_inst<false, true>(p, grid, st);
-  if (a_mn && !b_mn) return tc2_launch_inst<true, false>(p, grid, st);
-  return tc2_launch_inst<true, true>(p, grid, st);
+cudaError_t tc2_launch(bool a_mn, bool b_mn, bool noise, const TcParams& p, int grid, cudaStream_t st) {
+  if (noise) {      // only the first encoder layer carries noise: its forward (K-major A and B) and its wgrad (both MN-major)
+    if (!a_mn && !b_mn) return tc2_launch_inst<false, false, true>(p, grid, st);
+    if (a_mn && b_mn) return tc2_launch_inst<true, true, true>(p, grid, st);
+    return cudaErrorInvalidValue;
+  }
+  if (!a_mn && !b_mn) return tc2_launch_inst<false, false, false>(p, grid, st);
+  if (!a_mn && b_mn) return tc2_launch_inst<false, true, false>(p, grid, st);
+  if (a_mn && !b_mn) return tc2_launch_inst<true, false, false>(p, grid, st);
+  return tc2_launch_inst<true, true, false>(p, grid, st);
 }
 
 }  // namespace mmae

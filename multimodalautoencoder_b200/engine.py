@@ -453,6 +453,11 @@ class Engine:
         return self.lib.mmae_kernel_launches(self._h)
 
     @property
+    def fused_noise_launches(self):
+        """GEMM launches that applied the block mask + noise while loading their A operand (no noisy copy of X)."""
+        return self.lib.mmae_fused_noise_launches(self._h)
+
+    @property
     def graph_replays(self):
         """Train steps replayed from a captured CUDA graph."""
         return self.lib.mmae_graph_replays(self._h)

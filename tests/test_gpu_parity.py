@@ -114,6 +114,10 @@ CASES = [
     dict(id='tiny-ragged', kw=dict(num_feats=31, starts=T_STARTS, layers=(12, 6), lam=0.01)),
     dict(id='one-layer', kw=dict(layers=(64,), loss='mean_squared')),
     dict(id='linear-ce', kw=dict(act='linear', layers=(64, 32))),
+    # first layer wide enough for the two-SM GEMM: mask + noise applied to the A tile in shared memory (forward and wgrad),
+    # modality boundaries on / off 32-column chunks
+    dict(id='wide-first-layer-aligned', kw=dict(num_feats=512, starts=[0, 128, 192, 256, 384, 512], layers=(384, 64), tie=False, lam=0.001), B=640),
+    dict(id='wide-first-layer-ragged', kw=dict(num_feats=512, starts=[0, 100, 230, 300, 410, 512], layers=(320, 48), tie=True, act='relu', loss='mean_squared'), B=517),
 ]
 
 
@@ -121,7 +125,7 @@ CASES = [
 @pytest.mark.parametrize('case', CASES, ids=[c['id'] for c in CASES])
 def test_forward_backward_parity(case, prec):
     ocfg, ecfg = make_cfgs(precision=prec, **case['kw'])
-    B = 384 if ocfg.num_feats == 320 else 37
+    B = case.get('B', 384 if ocfg.num_feats == 320 else 37)
     rng, X = _data(ocfg, B, 2)
     P = O.init_params(ocfg, rng)
     e = _engine(ecfg, P)
@@ -168,6 +172,35 @@ def test_forward_backward_parity(case, prec):
     untouched = set(P) - set(G)
     for k in untouched:
         assert np.array_equal(e.get_variable(k), P[k].astype(np.float32)), k
+    e.close()
+
+
+@pytest.mark.parametrize('case', [c for c in CASES if c['id'].startswith('wide-first-layer')], ids=lambda c: c['id'])
+def test_noise_fused_into_operand_load(case, monkeypatch):
+    """MMAE_FUSE_NOISE=1: the two-SM GEMM applies block mask + zero noise to its A tile in shared memory (forward of the
+    first encoder layer and its wgrad) instead of reading a materialised noisy X; same loss and gradients."""
+    monkeypatch.setenv('MMAE_FUSE_NOISE', '1')
+    ocfg, ecfg = make_cfgs(precision='tf32', **case['kw'])
+    B = case['B']
+    rng, X = _data(ocfg, B, 2)
+    P = O.init_params(ocfg, rng)
+    e = _engine(ecfg, P)
+    zb, mb = PH.noise_descriptor(0, 0, B, ocfg.num_feats, len(ocfg.modality_names), int(ocfg.num_feats * .05), True,
+                                 PH.categorical_thresholds(ocfg.noise_p), e.type_masks, 1)
+    noisy = O.noise_from_descriptor(ocfg, X, zb, mb)
+    e.set_noise(zb, mb)
+    P2 = {k: v.copy() for k, v in P.items()}
+    c2, G = O.train_step(ocfg, P2, O.AdamState(), noisy, X)
+    e.train_step(X.astype(np.float32), noise=True)
+    assert e.fused_noise_launches >= 2, 'forward + wgrad of the first layer should have applied the noise in the operand load'
+    sc = e.scalars()
+    tol = TOL['tf32']
+    assert abs(sc['recon_loss'] - c2['recon_loss']) <= tol['loss'] * abs(c2['recon_loss'])
+    scale = sc['grad_scale'] if ocfg.loss_func == 'mean_squared' else 1.0
+    for k in ('weights0', 'encode_biases0'):
+        ok, info = _grad_ok(e.get_gradient(k).astype(np.float64) * scale, G[k] - (0.0 if 'bias' in k else
+                            (2 * ocfg.weight_penalty if ocfg.tie_weights else ocfg.weight_penalty) * P[k]), tol)
+        assert ok, (k, info)
     e.close()
 
 
