@@ -52,7 +52,6 @@ struct TcParams {
   int a3d, b3d;                 // MN-major operand loaded through a 3-D map (one TMA per stage)
   Epilogue ep;
   NoiseView nz;                 // two-SM kernel only: block-mask + zero noise applied to the A tile in shared memory
-  int l2_ahead;                 // two-SM kernel: k-blocks of A prefetched into L2 ahead of the shared-memory ring (0 = off)
   int nz_aligned;               // every modality boundary is a multiple of 32 columns (one modality per 32-column chunk)
 };
 
@@ -254,8 +253,6 @@ inline cudaError_t launch_gemm_tc2(bool ta, bool tb, const GemmArgs& g, const Tc
     p.C = g.C; p.ldc = g.ldc; p.split_stride = 0;
   }
   p.nz = g.noise; p.nz_aligned = g.noise_aligned32;
-  static const int l2a = getenv("MMAE_TC2_L2AHEAD") ? atoi(getenv("MMAE_TC2_L2AHEAD")) : 0;
-  p.l2_ahead = l2a;
   return tc2_launch(a_mn, b_mn, g.noise.enabled != 0, p, pl.grid, st);
 }
 

@@ -42,14 +42,6 @@ __device__ __forceinline__ void tma2_load_3d(const CUtensorMap* tm, uint32_t lea
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// L2 prefetch of a tile that will be loaded a few k-blocks from now: the shared-memory ring is only 6 stages deep, so the
-// HBM latency of A (activations stream from DRAM; the weights stay in L2) is taken out of the stage's critical path.
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 __device__ __forceinline__ void tc2_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -162,10 +154,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NOISE ? TC2_THREADS_
         const int m0 = mb * 256 + (int)rank * TC_BM;
         const int n0 = nb * TC2_BN + (int)rank * TC2_BN_HALF;
         for (int64_t k = kb0; k < kend; k += TC_BK) {
-          if (p.l2_ahead > 0) {
-            const int64_t kp = k + (int64_t)p.l2_ahead * TC_BK;
-            if (kp < kend) { if (!A_MN) tma_prefetch_2d(&p.tmA, (int)kp, m0); else tma_prefetch_3d(&p.tmA, 0, (int)kp, m0 / 32); }
-          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * TC2_STAGE_BYTES;
           uint8_t* sb = sa + TC2_ABYTES;
