@@ -424,6 +424,22 @@ struct mmae_engine {
     if (comm_stream) cudaStreamDestroy(comm_stream);
   }
 
+  // Refreshes every stale K-major weight shadow in one launch (called at the top of a tf32 forward pass).
+  int refresh_shadows() {
+    TransposeGroup g; g.n = 0; int tiles = 0;
+    for (size_t i = 0; i < vars.size() && g.n < TransposeGroup::kMax; ++i) {
+      Var& v = vars[i];
+      if (v.cols == 0 || !pt_dirty[i]) continue;
+      g.off[g.n] = v.off; g.rows[g.n] = (int)v.rows; g.cols[g.n] = (int)v.cols; g.tile0[g.n] = tiles;
+      tiles += (int)(((v.rows + 31) / 32) * ((v.cols + 31) / 32));
+      pt_dirty[i] = 0; ++g.n;
+    }
+    if (g.n == 0) return 0;
+    g.tile0[g.n] = tiles;
+    transpose_group_kernel<<<tiles, dim3(32, 8), 0, stream>>>(P, PT, g);
+    CKL("transpose_group");
+    return 0;
+  }
   // K-major shadow of a weight variable (refreshed lazily after set_variable / Adam); null if w is not a variable
   const float* shadowT(const float* w, int64_t rows, int64_t cols) {
     for (size_t i = 0; i < vars.size(); ++i) {
@@ -732,6 +748,7 @@ struct mmae_engine {
     const int act = cfg.activation;
     const float* a = o.X;
     NoiseView nv = noise_view(o.noise);
+    if (cfg.precision == MMAE_PREC_TF32 && B >= 32) RET(refresh_shadows());
     if (o.noise || o.train_recon || o.labels) RET(ensure_acts(B));
     // Wide first layers can go through the two-SM GEMM variant that applies the mask + noise to the A tile in shared
     // memory (forward and the layer's wgrad), so that no noisy copy of X is ever written.  Measured slower than one

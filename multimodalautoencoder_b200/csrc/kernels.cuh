@@ -102,6 +102,34 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
+// All stale weight shadows in ONE launch (a step used to issue one small transpose per weight matrix).
+struct TransposeGroup {
+  static constexpr int kMax = 16;
+  int n;
+  int64_t off[kMax];        // offset of the variable in P / PT
+  int rows[kMax], cols[kMax];
+  int tile0[kMax + 1];      // first 32 x 32 tile of each variable in the flattened grid
+};
+__global__ void transpose_group_kernel(const float* __restrict__ P, float* __restrict__ PT, const TransposeGroup g) {
+  __shared__ float t[32][33];
+  int v = 0;
+  while (v + 1 < g.n && (int)blockIdx.x >= g.tile0[v + 1]) ++v;
+  const int rows = g.rows[v], cols = g.cols[v];
+  const int tiles_c = (cols + 31) / 32;
+  const int tl = blockIdx.x - g.tile0[v];
+  const int c0 = (tl % tiles_c) * 32, r0 = (tl / tiles_c) * 32;
+  const float* in = P + g.off[v]; float* out = PT + g.off[v];
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < rows && c < cols) ? __ldg(in + (int64_t)r * cols + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(int64_t)c * rows + r] = t[threadIdx.x][i];
+  }
+}
+
 // ------------------------------------------------------------------ batch gather (data_funcs.py:167-168)
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
                                    float* __restrict__ dst, int64_t batch, int width) {
