@@ -6,7 +6,9 @@ src = open('scripts/time_small.py').read().split("for B in [int(x)")[0]
 exec(src)
 B = 2000000
 X = torch.rand((B, 320), device='cuda')
+X[::3, 200:220] = -1.0
 e = mk(1, B)
-e.forward(X, recon=True, loss=True)
+out = torch.empty_like(X)
+e.forward_into(X, filled=out)
 torch.cuda.synchronize()
 PY
