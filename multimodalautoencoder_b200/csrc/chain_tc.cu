@@ -19,7 +19,6 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
   } while (!done);
 }
-#define mbar_wait mbar_wait_parked
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity) {
   uint32_t done;
   do {
@@ -87,16 +86,6 @@ struct EpiStage {
   uint32_t aux_phase[2];
   uint32_t uses;          // tiles handed to TMA so far (alternates the two buffers)
 };
-// 1/d for d >= 1 on the FMA pipe: integer-trick seed (12 % error) + 3 Newton steps (6e-8).  The hidden epilogues sit on
-// the critical path of a tile and share the SM's 16-lane MUFU with the output epilogue's exp/log/rcp, so the
-// softsign divide must not queue behind them.
-__device__ __forceinline__ float rcp_nr(float d) {
-  float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
-  r = r * fmaf(-d, r, 2.f);
-  r = r * fmaf(-d, r, 2.f);
-  r = r * fmaf(-d, r, 2.f);
-  return r;
-}
 // .ftz forms: without them every ex2 / lg2 / rcp drags a denormal-rescaling FSETP + FMUL + FSEL sequence along
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -326,7 +315,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
       const uint64_t pol_keep = l2_policy_evict_last();
       for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x) {
         for (int k = 0; k < K0; k += TC_BK) {
-          mbar_wait(&xempty[stage], phase ^ 1);
+          mbar_wait_parked(&xempty[stage], phase ^ 1);
           mbar_expect_tx(&xfull[stage], CH_XBYTES);
           tma_load_2d_hint(&p.tmA, &xfull[stage], xring + stage * CH_XBYTES, k, t * TC_BM, pol_keep);
           if (++stage == p.x_stages) { stage = 0; phase ^= 1; }
@@ -381,7 +370,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
         for (int i = 0; i < nops; ++i) {
           const int K = p.op[i].K, a_tmem = p.op[i].a_tmem, n_chunk = p.op[i].n_chunk, n_chunks = p.op[i].n_chunks;
           const uint32_t d_col = (uint32_t)p.op[i].d_col, a_col = (uint32_t)p.op[i].a_col;
-          if (i == last && it > 0) { mbar_wait(last_done, par ^ 1); tc_fence_after(); }   // previous tile's result drained
+          if (i == last && it > 0) { mbar_wait_parked(last_done, par ^ 1); tc_fence_after(); }   // previous tile's result drained
           const uint32_t idesc = idesc_tf32_rt(TC_BM, n_chunk);
           const uint32_t cd_s = smem_u32(&chunk_done[(i > 0 ? i - 1 : 0) * CH_MAX_CHUNKS]);
           if (p.trace && blockIdx.x == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 0] = clock64();
@@ -443,7 +432,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
         const int r = ew * 16 + (lane & 15), hq = (lane >> 4) * 4;
         float carry = 0.f; uint32_t bits = 0u; int m = 0;
         for (int k0 = 0; k0 < K0; k0 += TC_BK) {
-          mbar_wait(&xfull[sxs], sxph);
+          mbar_wait_parked(&xfull[sxs], sxph);
           const uint32_t base = xring_s + sxs * CH_XBYTES + r * 128;
           const int kend = k0 + TC_BK;
           float4 f[4];
@@ -469,14 +458,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
             else { carry += part; break; }
           }
         }
-        if (it >= 2) mbar_wait(&miss_free[it & 1], ((it >> 1) - 1) & 1);      // the tile that last used this slot is drained
+        if (it >= 2) mbar_wait_parked(&miss_free[it & 1], ((it >> 1) - 1) & 1);      // the tile that last used this slot is drained
         if (lane < 16) miss_s[(it & 1) * 128 + r] = bits;
         __syncwarp();
         if (lane == 0) mbar_arrive(&miss_ready[it & 1]);
       }
       for (int i = 0; i < last; ++i) {
         const ChainOp& o = p.op[i];
-        mbar_wait(&mma_done[i], par);
+        mbar_wait_parked(&mma_done[i], par);
         tc_fence_after();
         if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 2] = clock64();
         const int chunks = o.n_chunk / 32;
@@ -523,12 +512,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
         }
         __syncwarp();
       }
-      mbar_wait(&mma_done[last], par);
+      mbar_wait_parked(&mma_done[last], par);
       tc_fence_after();
       if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + last) * 4 + 2] = clock64();
       const bool row_valid = (int64_t)row0 + lane < p.M;
       uint32_t miss = 0u;
-      if (p.scan_miss) { mbar_wait(&miss_ready[it & 1], (it >> 1) & 1); miss = miss_s[(it & 1) * 128 + quad * 32 + lane]; }
+      if (p.scan_miss) { mbar_wait_parked(&miss_ready[it & 1], (it >> 1) & 1); miss = miss_s[(it & 1) * 128 + quad * 32 + lane]; }
       else if (lo.ep.fill_bits && row_valid) miss = __ldg(lo.ep.fill_bits + row0 + lane);
       for (int ch = half; ch < lchunks; ch += 2) {
         if (ch * 32 >= lo.N) break;                                   // padding columns only
@@ -545,10 +534,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
         }
-        if (has_aux) { mbar_wait(es.aux_bar[b], es.aux_phase[b]); es.aux_phase[b] ^= 1; }
+        if (has_aux) { mbar_wait_parked(es.aux_bar[b], es.aux_phase[b]); es.aux_phase[b] ^= 1; }
         uint8_t* tile_p = es.buf[b];
         const uint32_t tile = smem_u32(tile_p);
-        if (p.dbg & 1) {} else
         if (lo.ep.mode == EPI_LOSS_TRAIN) {
           if (has_aux) chain_final_dispatch<EPI_LOSS_TRAIN, true>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc);
           else chain_final_dispatch<EPI_LOSS_TRAIN, false>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc);

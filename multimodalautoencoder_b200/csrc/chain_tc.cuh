@@ -80,7 +80,6 @@ struct ChainParams {
   int scan_miss, num_mod; const int32_t* starts;
   unsigned stagger_ns; // per-CTA start offset step: CTAs that all start together also all load / compute / store together,
                        // so HBM and L2 see bursts; offsetting them over one tile period smooths the demand (0 = off)
-  int dbg;             // debug switches (MMAE_CHAIN_DBG): 1 = output epilogue skips its math
   long long* trace;    // debug: clock64 stamps of CTA 0 ([tile it][op][4]: mma start, mma issued, epi start, epi end), or null
 };
 

@@ -711,8 +711,6 @@ struct mmae_engine {
     if (o.fill_out && M <= 32) { cp.scan_miss = 1; cp.num_mod = M; cp.starts = d_starts; }
     const int grid = std::min(cp.m_tiles, num_sms);
     static const bool want_trace = getenv("MMAE_CHAIN_TRACE") != nullptr;
-    static const int chain_dbg = getenv("MMAE_CHAIN_DBG") ? atoi(getenv("MMAE_CHAIN_DBG")) : 0;
-    cp.dbg = chain_dbg;
     static const int chain_stagger = getenv("MMAE_CHAIN_STAGGER") ? atoi(getenv("MMAE_CHAIN_STAGGER")) : 60;
     cp.stagger_ns = cp.m_tiles >= 8 * grid ? (unsigned)chain_stagger : 0u;
     long long* trace = nullptr;
