@@ -13,7 +13,7 @@
 
 namespace mmae {
 
-constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_THREADS = 256;
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 32, SG_THREADS = 256;
 
 struct GemmArgs {
   int64_t M, N, K;
@@ -47,12 +47,15 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const GemmArgs g)
   const int64_t kbeg = g.splits > 1 ? (int64_t)blockIdx.z * g.k_per_split : 0;
   const int64_t kend = g.splits > 1 ? min(g.K, kbeg + g.k_per_split) : g.K;
   float* Cout = g.splits > 1 ? g.C + (int64_t)blockIdx.z * g.M * g.N : g.C;
-  for (int64_t k0 = kbeg; k0 < kend; k0 += SG_BK) {
-    // ---- A tile -> As[k][m]
+  // Register-prefetched K loop: the global loads of tile k+1 are in flight while tile k is multiplied out of shared
+  // memory.  Small-batch steps (M = 20..100) run a handful of CTAs per GEMM, so each CTA's loop latency is the step time.
+  constexpr int LPT = SG_BM * SG_BK / SG_THREADS;      // elements of each operand tile per thread (8)
+  float ra[LPT], rb[LPT];
+  auto fetch = [&](int64_t k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < LPT; ++i) {
       int m, k;
-      if (!TA) { k = tid & 15; m = (tid >> 4) + 16 * i; }     // K contiguous in memory
+      if (!TA) { k = tid & 31; m = (tid >> 5) + 8 * i; }      // K contiguous in memory
       else     { m = tid & 63; k = (tid >> 6) + 4 * i; }      // M contiguous in memory
       int64_t gm = m0 + m, gk = k0 + k;
       float v = 0.f;
@@ -60,20 +63,31 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const GemmArgs g)
         if (!TA) { v = __ldg(g.A + gm * g.lda + gk); v = noisy_value(g.noise, gm, (int)gk, v); }
         else     { v = __ldg(g.A + gk * g.lda + gm); v = noisy_value(g.noise, gk, (int)gm, v); }
       }
-      As[k][m] = v;
+      ra[i] = v;
     }
-    // ---- B tile -> Bs[k][n]
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < LPT; ++i) {
       int n, k;
       if (!TB) { n = tid & 63; k = (tid >> 6) + 4 * i; }      // N contiguous
-      else     { k = tid & 15; n = (tid >> 4) + 16 * i; }     // K contiguous
+      else     { k = tid & 31; n = (tid >> 5) + 8 * i; }      // K contiguous
       int64_t gn = n0 + n, gk = k0 + k;
       float v = 0.f;
       if (gn < g.N && gk < kend) v = !TB ? __ldg(g.B + gk * g.ldb + gn) : __ldg(g.B + gn * g.ldb + gk);
-      Bs[k][n] = v;
+      rb[i] = v;
     }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < LPT; ++i) {
+      if (!TA) As[tid & 31][(tid >> 5) + 8 * i] = ra[i]; else As[(tid >> 6) + 4 * i][tid & 63] = ra[i];
+      if (!TB) Bs[(tid >> 6) + 4 * i][tid & 63] = rb[i]; else Bs[tid & 31][(tid >> 5) + 8 * i] = rb[i];
+    }
+  };
+  if (kbeg < kend) fetch(kbeg);
+  for (int64_t k0 = kbeg; k0 < kend; k0 += SG_BK) {
+    stash();
     __syncthreads();
+    if (k0 + SG_BK < kend) fetch(k0 + SG_BK);
 #pragma unroll
     for (int k = 0; k < SG_BK; ++k) {
       float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
