@@ -391,6 +391,17 @@ struct mmae_engine {
     return 0;
   }
 
+  int* tile_counters = nullptr; int64_t counters_cap = 0;
+  int ensure_counters(int64_t count) {
+    if (count <= counters_cap) return 0;
+    CK(cudaStreamSynchronize(stream));
+    clear_graphs();
+    const int64_t nc = std::max<int64_t>(count, 1024);
+    RET(realloc_dev(tile_counters, nc));
+    CK(cudaMemset(tile_counters, 0, nc * sizeof(int)));
+    counters_cap = nc;
+    return 0;
+  }
   int ensure_splitk(int64_t count) {
     if (count <= splitk_cap) return 0;
     CK(cudaStreamSynchronize(stream));
@@ -407,7 +418,7 @@ struct mmae_engine {
     fr(noisy);
     for (auto p : ea) fr(p); for (auto p : da) fr(p); for (auto p : ha) fr(p);
     fr(mu); fr(lv); fr(eps); fr(emb); fr(glv); fr(out); fr(dA); fr(dB);
-    fr(hlogits); fr(hdelta); fr(hprobs); fr(hpreds); fr(partials); fr(colsum_ws); fr(splitk_ws); fr(d_idx);
+    fr(hlogits); fr(hdelta); fr(hprobs); fr(hpreds); fr(partials); fr(colsum_ws); fr(splitk_ws); fr(tile_counters); fr(d_idx);
     for (int i = 0; i < 2; ++i) { if (xin_free[i]) cudaEventDestroy(xin_free[i]); if (xin_ready[i]) cudaEventDestroy(xin_ready[i]); }
     for (auto& r : prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -504,23 +515,22 @@ struct mmae_engine {
       return 0;
     }
     g.ep.colsum_partials = nullptr;
-    g.splits = 1; g.k_per_split = 0;
-    if (allow_splitk && ep.mode == EPI_PLAIN) {
+    g.splits = 1; g.k_per_split = 0; g.ws = nullptr; g.tile_counters = nullptr;
+    {      // in-kernel split-K (any epilogue): the last CTA of a tile reduces the slices and finishes the tile
       const int s = simt_pick_splits(m, n, k, num_sms);
       if (s > 1) {
-        RET(ensure_splitk((int64_t)s * m * n));
-        g.splits = s; g.k_per_split = (((k + s - 1) / s + SG_BK - 1) / SG_BK) * SG_BK;
+        const int64_t tiles = gemm_simt_num_ctas(m, n);
+        RET(ensure_splitk((int64_t)s * tiles * SG_BM * SG_BN));
+        RET(ensure_counters(tiles));
+        g.k_per_split = (((k + s - 1) / s + SG_BK - 1) / SG_BK) * SG_BK;
         g.splits = (int)((k + g.k_per_split - 1) / g.k_per_split);
-        g.C = splitk_ws; g.ldc = n; g.ep.beta = 0.f;
+        g.ws = splitk_ws; g.tile_counters = tile_counters;
       }
     }
+    (void)allow_splitk;
     cudaError_t e = launch_gemm_simt(ta, tb, g, stream);
     ++launches;
     if (e != cudaSuccess) return cuda_fail(e, "simt gemm launch");
-    if (g.splits > 1) {
-      splitk_reduce_kernel<<<grid_for(m * n, 256), 256, 0, stream>>>(splitk_ws, m * n, g.splits, Cp, n, ldc, ep.beta);
-      CKL("splitk_reduce");
-    }
     if (n_partials) *n_partials = gemm_simt_num_ctas(m, n);
     return 0;
   }

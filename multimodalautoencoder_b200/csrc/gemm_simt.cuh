@@ -23,8 +23,10 @@ struct GemmArgs {
   NoiseView noise;      // applied to A's stored (row, col) = (batch row, feature) when enabled
   int noise_aligned32 = 0;   // modality boundaries are multiples of 32 columns (two-SM tcgen05 patch fast path)
   Epilogue ep;
-  int splits;           // split-K over blockIdx.z (EPI_PLAIN only): slice z of C lives at C + z*M*N with ldc = N
-  int64_t k_per_split;
+  int splits;           // split-K over blockIdx.z: the CTAs of one output tile write their partial tiles to `ws`, the last one
+  int64_t k_per_split;  //   to arrive (per-tile counter) adds them up in slice order and runs the epilogue: one launch,
+  float* ws;            //   deterministic, and small-batch GEMMs (M = 20..100: one or two tiles) still fill the SMs
+  int* tile_counters;   //   zero on entry, reset by the reducing CTA
 };
 
 template <bool TA, bool TB>
@@ -46,7 +48,6 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const GemmArgs g)
 
   const int64_t kbeg = g.splits > 1 ? (int64_t)blockIdx.z * g.k_per_split : 0;
   const int64_t kend = g.splits > 1 ? min(g.K, kbeg + g.k_per_split) : g.K;
-  float* Cout = g.splits > 1 ? g.C + (int64_t)blockIdx.z * g.M * g.N : g.C;
   // Register-prefetched K loop: the global loads of tile k+1 are in flight while tile k is multiplied out of shared
   // memory.  Small-batch steps (M = 20..100) run a handful of CTAs per GEMM, so each CTA's loop latency is the step time.
   constexpr int LPT = SG_BM * SG_BK / SG_THREADS;      // elements of each operand tile per thread (8)
@@ -101,6 +102,38 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const GemmArgs g)
     __syncthreads();
   }
 
+  if (g.splits > 1) {
+    // partial tile -> workspace [tile][slice][64 x 64]; the last CTA of the tile sums the slices in order
+    __shared__ int is_last;
+    const int64_t tile = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+    float* wt = g.ws + (tile * g.splits + blockIdx.z) * (SG_BM * SG_BN);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(wt + (ty * 4 + i) * SG_BN + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int prev = atomicAdd(g.tile_counters + tile, 1);
+      is_last = prev == g.splits - 1;
+      if (is_last) g.tile_counters[tile] = 0;            // ready for the next launch
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const float* w0 = g.ws + tile * g.splits * (SG_BM * SG_BN);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int z = 0; z < g.splits; ++z) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(w0 + (int64_t)z * (SG_BM * SG_BN) + (ty * 4 + i) * SG_BN + tx * 4));
+        acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+      }
+    }
+  }
+  float* Cout = g.C;
   float loss_acc = 0.f;
   int64_t ldaux; const float* auxp = epilogue_aux_ptr(g.ep, &ldaux);
   float bias_v[4];
@@ -143,9 +176,9 @@ inline int64_t gemm_simt_num_ctas(int64_t M, int64_t N) {
 // Split count for a CUDA-core wgrad whose tile grid would leave most SMs idle (K = batch is the long dimension).
 inline int simt_pick_splits(int64_t M, int64_t N, int64_t K, int num_sms) {
   const int64_t tiles = gemm_simt_num_ctas(M, N);
-  if (tiles >= num_sms || K < 512) return 1;
-  int64_t s = (2 * num_sms + tiles - 1) / tiles;
-  const int64_t max_s = K / 128;        // >= 8 k-iterations per slice
+  if (tiles >= num_sms || K < 128) return 1;
+  int64_t s = (num_sms + tiles - 1) / tiles;
+  const int64_t max_s = K / 64;         // >= 2 k-iterations per slice
   if (s > max_s) s = max_s;
   if (s > 64) s = 64;
   return (int)(s < 1 ? 1 : s);
