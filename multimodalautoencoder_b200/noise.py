@@ -42,17 +42,31 @@ def numpy_descriptor(batch, num_feats, n_mod, intelligent, noise_p=None, type_ma
     n_zero = int(num_feats * .05)
     zero_bits = np.zeros((batch, zw), np.uint32)
     mod_bits = np.zeros(batch, np.uint32)
-    for r in range(batch):
-        cols = rng.choice(num_feats, size=n_zero)
-        np.bitwise_or.at(zero_bits[r], cols >> 5, (1 << (cols & 31)).astype(np.uint32))
-        if intelligent:
-            k = int(np.argmax(rng.multinomial(1, pvals=noise_p)))
-            mod_bits[r] = type_masks[k] if override_mask is None else override_mask     # :691-692
+    # The RNG calls stay one row at a time, in the reference's order; everything else is batched.  In the legacy
+    # RandomState stream choice(F, size=k) IS randint(0, F, size=k) (choice's replace=True, p=None branch), which
+    # skips choice's argument handling (13 -> 9 us per row here).
+    cols_all = np.empty((batch, n_zero), np.int64)
+    randint, multinomial = rng.randint, rng.multinomial
+    if intelligent:
+        ks = np.empty(batch, np.int64)
+        for r in range(batch):
+            cols_all[r] = randint(0, num_feats, n_zero)
+            ks[r] = multinomial(1, noise_p).argmax()
+        if override_mask is None:
+            mod_bits[:] = np.asarray(type_masks, np.uint32)[ks]
         else:
+            mod_bits[:] = override_mask                                                     # :691-692
+    else:
+        for r in range(batch):
+            cols_all[r] = randint(0, num_feats, n_zero)
             m = 0
             for _ in range(num_drop):
-                m |= 1 << int(rng.randint(0, n_mod))
+                m |= 1 << int(randint(0, n_mod))
             mod_bits[r] = m
+    if n_zero:
+        flat = cols_all.ravel()
+        rows = np.repeat(np.arange(batch), n_zero)
+        np.bitwise_or.at(zero_bits, (rows, flat >> 5), (np.uint32(1) << (flat & 31).astype(np.uint32)))
     return zero_bits, mod_bits
 
 
