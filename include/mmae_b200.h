@@ -165,7 +165,8 @@ int mmae_train_step_pair(mmae_engine* e, const float* X_in_dev, const float* tar
 int mmae_cls_train_step(mmae_engine* e, const float* X_dev, const float* labels_dev, int64_t batch,
                         int use_noise, float keep);
 /* Same two steps fed from HOST buffers (what feed_dict does): pinned-or-pageable fp32 in,
- * H2D inside the call.  Philox noise is drawn on the device when gen_noise != 0. */
+ * H2D inside the call.  gen_noise: 0 = clean input, 1 = Philox noise drawn on the device for this step,
+ * 2 = apply the descriptor last given to mmae_set_noise (host RNG, reference order). */
 int mmae_train_step_host(mmae_engine* e, const float* X_host, int64_t batch, int gen_noise, float keep);
 int mmae_cls_train_step_host(mmae_engine* e, const float* X_host, const float* labels_host,
                              int64_t batch, int gen_noise, float keep);

@@ -133,6 +133,10 @@ struct mmae_engine {
   int graph_mode = -1;
   int64_t graph_replays = 0;
 
+  // ---- pinned staging of host-drawn noise descriptors (rng_mode='numpy'): no stream synchronisation per step
+  uint32_t* h_noise[2] = {nullptr, nullptr}; int64_t h_noise_cap = 0; int h_noise_turn = 0;
+  cudaEvent_t h_noise_done[2] = {nullptr, nullptr};
+
   // ---- RNG / sharding
   uint64_t rng_step = 0;
   uint32_t cur_step = 0;                          // step used by the in-flight forward/backward pair
@@ -424,6 +428,7 @@ struct mmae_engine {
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (gstream) cudaStreamDestroy(gstream);
     if (d2h_stream) cudaStreamDestroy(d2h_stream);
+    for (int i = 0; i < 2; ++i) { if (h_noise[i]) cudaFreeHost(h_noise[i]); if (h_noise_done[i]) cudaEventDestroy(h_noise_done[i]); }
     for (int i = 0; i < 2; ++i) {
       for (int j = 0; j < 3; ++j) if (pipe_out[i][j]) cudaFree(pipe_out[i][j]);
       if (pipe_ready[i]) cudaEventDestroy(pipe_ready[i]);
@@ -1233,9 +1238,30 @@ int mmae_set_noise(mmae_engine* e, const uint32_t* zero_bits_host, const uint32_
   if (!zero_bits_host || !mod_bits_host || batch <= 0) return e->fail(MMAE_ERR_INVALID, "null descriptor");
   int r = e->ensure_cap(batch); if (r) return r;
   const int zw = (e->F + 31) / 32;
-  cudaError_t ce = cudaMemcpyAsync(e->zero_bits, zero_bits_host, (size_t)batch * zw * 4, cudaMemcpyHostToDevice, e->stream);
-  if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->mod_bits, mod_bits_host, (size_t)batch * 4, cudaMemcpyHostToDevice, e->stream);
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);     // host buffers may be pageable / reused
+  // The caller's arrays may be pageable and reused right away: copy them into one of two pinned staging buffers and
+  // let the H2D run asynchronously on the engine's stream (a per-step stream synchronisation here would serialise
+  // the host-side noise drawing of step s+1 with the device work of step s).
+  const int64_t words = batch * (int64_t)(zw + 1);
+  cudaError_t ce = cudaSuccess;
+  if (words > e->h_noise_cap) {
+    ce = cudaStreamSynchronize(e->stream);
+    for (int i = 0; i < 2 && ce == cudaSuccess; ++i) {
+      if (e->h_noise[i]) cudaFreeHost(e->h_noise[i]);
+      ce = cudaMallocHost(&e->h_noise[i], (size_t)words * 4 * 2);
+      if (ce == cudaSuccess && !e->h_noise_done[i]) ce = cudaEventCreateWithFlags(&e->h_noise_done[i], cudaEventDisableTiming);
+    }
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "set_noise staging");
+    e->h_noise_cap = words * 2;
+  }
+  const int t = e->h_noise_turn; e->h_noise_turn ^= 1;
+  ce = cudaEventSynchronize(e->h_noise_done[t]);            // the copy that last used this staging buffer is done
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "set_noise wait");
+  uint32_t* hz = e->h_noise[t]; uint32_t* hm = hz + batch * zw;
+  memcpy(hz, zero_bits_host, (size_t)batch * zw * 4);
+  memcpy(hm, mod_bits_host, (size_t)batch * 4);
+  ce = cudaMemcpyAsync(e->zero_bits, hz, (size_t)batch * zw * 4, cudaMemcpyHostToDevice, e->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->mod_bits, hm, (size_t)batch * 4, cudaMemcpyHostToDevice, e->stream);
+  if (ce == cudaSuccess) ce = cudaEventRecord(e->h_noise_done[t], e->stream);
   if (ce != cudaSuccess) return e->cuda_fail(ce, "set_noise");
   e->noise_rows = batch;
   return 0;
@@ -1408,7 +1434,7 @@ int mmae_train_step_host(mmae_engine* e, const float* X_host, int64_t batch, int
   ENTER(e);
   float* Xd = nullptr;
   int t = stage_host(e, X_host, nullptr, batch, 0, &Xd, nullptr); if (t < 0) return t;
-  if (gen_noise) { int r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }
+  if (gen_noise == 1) { int r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }      // 2: descriptor from mmae_set_noise
   int r = train_graphed(e, Xd, nullptr, batch, gen_noise ? 1 : 0, keep); if (r) return r;
   return release_stage(e, t);
 }
@@ -1419,7 +1445,7 @@ int mmae_cls_train_step_host(mmae_engine* e, const float* X_host, const float* l
   float *Xd = nullptr, *Yd = nullptr;
   const int ycols = e->cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? e->C : 1;
   int t = stage_host(e, X_host, labels_host, batch, ycols, &Xd, &Yd); if (t < 0) return t;
-  if (gen_noise) { int r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }
+  if (gen_noise == 1) { int r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }
   int r = cls_graphed(e, Xd, Yd, batch, gen_noise ? 1 : 0, keep); if (r) return r;
   return release_stage(e, t);
 }

@@ -310,15 +310,16 @@ class Engine:
         self._ck(self.lib.mmae_cls_train_step(self._h, C.c_void_p(X.data_ptr()), C.c_void_p(Y.data_ptr()),
                                               X.shape[0], int(bool(noise)), float(keep)))
 
-    def train_step_host(self, X_host, gen_noise=False, keep=1.0):
-        """X_host: C-contiguous float32 ndarray or pinned CPU tensor (kept alive by the caller until synchronize())."""
+    def train_step_host(self, X_host, gen_noise=False, keep=1.0, use_noise=False):
+        """X_host: C-contiguous float32 ndarray or pinned CPU tensor (kept alive by the caller until synchronize()).
+        gen_noise: Philox noise drawn on the device; use_noise: apply the descriptor last given to set_noise."""
         ptr, B = self._host_ptr(X_host)
-        self._ck(self.lib.mmae_train_step_host(self._h, ptr, B, int(bool(gen_noise)), float(keep)))
+        self._ck(self.lib.mmae_train_step_host(self._h, ptr, B, 1 if gen_noise else (2 if use_noise else 0), float(keep)))
 
-    def cls_train_step_host(self, X_host, Y_host, gen_noise=False, keep=1.0):
+    def cls_train_step_host(self, X_host, Y_host, gen_noise=False, keep=1.0, use_noise=False):
         ptr, B = self._host_ptr(X_host)
         yptr, _ = self._host_ptr(Y_host)
-        self._ck(self.lib.mmae_cls_train_step_host(self._h, ptr, yptr, B, int(bool(gen_noise)), float(keep)))
+        self._ck(self.lib.mmae_cls_train_step_host(self._h, ptr, yptr, B, 1 if gen_noise else (2 if use_noise else 0), float(keep)))
 
     def _host_ptr(self, a):
         torch = self._torch

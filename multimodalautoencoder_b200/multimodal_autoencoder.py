@@ -341,7 +341,7 @@ class MultimodalAutoencoder:
                     print("\t Validation loss", val_loss)
             if step > 0 and step % self.save_every_nth == 0:
                 self.save_model()
-            eng.train_step(X, noise=True, keep=self.dropout_prob)
+            eng.train_step_host(X, use_noise=True, keep=self.dropout_prob)      # staged input: fixed device buffers -> graph replay
 
     def _train_resident(self, num_steps, classification):
         """rng_mode='philox': the training matrix lives on the device, every step samples its rows, draws its
@@ -409,7 +409,7 @@ class MultimodalAutoencoder:
                     print("\t Training accuracy", train_acc, "\t Validation accuracy", val_acc)
             if step > 0 and step % self.save_every_nth == 0:
                 self.save_model()
-            eng.cls_train_step(X, Y, noise=True, keep=self.classification_dropout_prob)
+            eng.cls_train_step_host(X, Y, use_noise=True, keep=self.classification_dropout_prob)
 
     def evaluate_performance(self, train_feed_dict=None):
         """(train loss, validation loss) on one batch each; validation batch of 200 with noise (:704-737)."""
