@@ -586,13 +586,15 @@ struct mmae_engine {
     return 0;
   }
 
+  bool step_synced = true;       // device StepState.step == (uint32_t)rng_step
   int advance_step() {
     rng_step += 1;
     advance_step_kernel<<<1, 1, 0, stream>>>(d_state); CKL("advance_step");
     return 0;
   }
   int set_step(uint64_t step) {
-    rng_step = step;
+    if (step == rng_step && step_synced) return 0;      // the device copy already holds it (advance_step keeps both in sync)
+    rng_step = step; step_synced = true;
     const uint32_t v = (uint32_t)step;
     CK(cudaMemcpyAsync(&d_state->step, &v, 4, cudaMemcpyHostToDevice, stream));    // pageable source: staged before return
     return 0;
@@ -1586,28 +1588,37 @@ int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, 
   ENTER(e);
   if (slot < 0 || slot > 1 || !e->ds_X[slot]) return e->fail(MMAE_ERR_STATE, "dataset slot is empty");
   if (classification && !e->ds_Y[slot]) return e->fail(MMAE_ERR_STATE, "dataset slot has no labels");
+  if (classification && e->H == 0) return e->fail(MMAE_ERR_STATE, "engine was created without a classification head");
   int r = e->ensure_host(batch); if (r) return r;
-  cudaError_t ce;
-  if (idx_host) {
-    ce = cudaMemcpyAsync(e->d_idx, idx_host, (size_t)batch * 8, cudaMemcpyHostToDevice, e->stream);
-    if (ce != cudaSuccess) return e->cuda_fail(ce, "H2D indices");
-  } else {
-    philox_indices_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, e->stream>>>(e->d_idx, batch, e->first_row,
-                                                                                (uint32_t)e->ds_rows[slot], &e->d_state->step, e->cfg.seed);
+  r = e->ensure_cap(batch); if (r) return r;
+  // device-side sampling (Philox row indices, gather, Philox noise) + the optimizer step: every per-step value comes
+  // from StepState in device memory, so the whole sequence replays as one graph
+  auto body = [&]() -> int {
+    cudaError_t ce;
+    if (idx_host) {
+      ce = cudaMemcpyAsync(e->d_idx, idx_host, (size_t)batch * 8, cudaMemcpyHostToDevice, e->stream);
+      if (ce != cudaSuccess) return e->cuda_fail(ce, "H2D indices");
+    } else {
+      philox_indices_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, e->stream>>>(e->d_idx, batch, e->first_row,
+                                                                                  (uint32_t)e->ds_rows[slot], &e->d_state->step, e->cfg.seed);
+      ++e->launches;
+    }
+    const int wpb = 8;
+    gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_X[slot], e->d_idx, e->xin[0], batch, e->F);
     ++e->launches;
-  }
-  const int wpb = 8;
-  gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_X[slot], e->d_idx, e->xin[0], batch, e->F);
-  ++e->launches;
-  if (classification) {
-    gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_Y[slot], e->d_idx, e->yin[0], batch, e->ds_ycols[slot]);
-    ++e->launches;
-  }
-  ce = cudaGetLastError();
-  if (ce != cudaSuccess) return e->cuda_fail(ce, "gather");
-  if (gen_noise) { r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }
-  if (classification) return mmae_cls_train_step(e, e->xin[0], e->yin[0], batch, gen_noise ? 1 : 0, keep);
-  return mmae_train_step(e, e->xin[0], batch, gen_noise ? 1 : 0, keep);
+    if (classification) {
+      gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_Y[slot], e->d_idx, e->yin[0], batch, e->ds_ycols[slot]);
+      ++e->launches;
+    }
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "gather");
+    if (gen_noise) { int rr = launch_noise_gen(e, batch, e->first_row); if (rr) return rr; }
+    return classification ? cls_core(e, e->xin[0], e->yin[0], batch, gen_noise ? 1 : 0, keep)
+                          : train_core(e, e->xin[0], nullptr, batch, gen_noise ? 1 : 0, keep);
+  };
+  if (idx_host || e->sticky) return body();            // host-supplied indices: pageable copy, stay eager
+  return e->run_graphed(graph_key(e, 2 + slot * 2 + (classification ? 1 : 0), e->ds_X[slot], e->ds_Y[slot], nullptr, batch, gen_noise ? 1 : 0, keep),
+                        classification ? 1 : 0, batch, body);
 }
 
 int mmae_read_scalars(mmae_engine* e, double* out, int count) {
