@@ -587,8 +587,9 @@ struct mmae_engine {
   }
 
   bool step_synced = true;       // device StepState.step == (uint32_t)rng_step
-  int advance_step() {
+  int advance_step(bool on_device = true) {
     rng_step += 1;
+    if (!on_device) return 0;       // the caller folds the device-side increment into finalize_scalars
     advance_step_kernel<<<1, 1, 0, stream>>>(d_state); CKL("advance_step");
     return 0;
   }
@@ -1027,20 +1028,26 @@ struct mmae_engine {
     return 0;
   }
   int allreduce_grads() { return join_comm(); }
-  int finalize_scalars(int64_t B, bool recon, bool headl) {
+  // fuse_opt >= 0: the kernel also advances that optimizer's step count / alpha (adam_prep) and, with fuse_advance, the
+  // Philox step -- two launches fewer per train step.
+  int finalize_scalars(int64_t B, bool recon, bool headl, int fuse_opt = -1, bool fuse_advance = false) {
     FinalizeArgs a; a.sums = d_sums; a.scalars = d_scalars; a.loss = cfg.loss_func; a.variational = cfg.variational;
+    a.state = (fuse_opt >= 0 || fuse_advance) ? d_state : nullptr; a.prep_opt = fuse_opt; a.advance = fuse_advance ? 1 : 0;
+    a.lr = fuse_opt == 1 ? cfg.head_learning_rate : cfg.learning_rate; a.b1 = cfg.beta1; a.b2 = cfg.beta2;
     a.n_elems = (double)gbatch(B) * F; a.batch = (double)gbatch(B);
     a.head_count = cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? (double)gbatch(B) * std::max(C, 1) : (double)gbatch(B);
     a.do_recon = recon ? 1 : 0; a.do_head = headl ? 1 : 0;
     finalize_scalars_kernel<<<1, 1, 0, stream>>>(a); CKL("finalize_scalars"); return 0;
   }
 
-  int apply_update(int opt, int64_t B) {
+  int apply_update(int opt, int64_t B, bool prep_done = false) {
     if (opt == 1 && H == 0) return fail(MMAE_ERR_STATE, "no classification head");
     t_opt[opt] += 1;
     const double lr = opt == 0 ? cfg.learning_rate : cfg.head_learning_rate;
-    adam_prep_kernel<<<1, 1, 0, stream>>>(d_state, opt, lr, (double)cfg.beta1, (double)cfg.beta2);
-    CKL("adam_prep");
+    if (!prep_done) {
+      adam_prep_kernel<<<1, 1, 0, stream>>>(d_state, opt, lr, (double)cfg.beta1, (double)cfg.beta2);
+      CKL("adam_prep");
+    }
     AdamArgs a; a.P = P; a.G = G;
     a.M = opt == 0 ? M0 : M1; a.V = opt == 0 ? V0 : V1;
     a.begin = opt == 0 ? 0 : enc_begin; a.end = opt == 0 ? enc_end : nP;
@@ -1089,7 +1096,7 @@ int launch_noise_gen(mmae_engine* e, int64_t batch, int64_t first_row) {
   return 0;
 }
 
-int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float keep, const float* target = nullptr) {
+int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float keep, const float* target = nullptr, bool defer_advance = false) {
   int r = e->begin_step(B, use_noise != 0); if (r) return r;
   mmae_engine::FwdOpts o; o.X = X; o.target = target ? target : X; o.labels = nullptr; o.B = B; o.noise = use_noise != 0; o.keep = keep;
   o.train_recon = true; o.decoder = true; o.headp = false; o.recon_out = nullptr;
@@ -1097,10 +1104,10 @@ int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float kee
   r = e->sums_allreduce(); if (r) return r;          // overlaps the whole backward pass
   r = e->backward_recon(B, keep); if (r) return r;
   e->last_B = B;
-  return e->advance_step();
+  return e->advance_step(!defer_advance);
 }
 
-int do_cls(mmae_engine* e, const float* X, const float* Y, int64_t B, int use_noise, float keep) {
+int do_cls(mmae_engine* e, const float* X, const float* Y, int64_t B, int use_noise, float keep, bool defer_advance = false) {
   if (e->H == 0) return e->fail(MMAE_ERR_STATE, "engine was created without a classification head");
   int r = e->begin_step(B, use_noise != 0); if (r) return r;
   mmae_engine::FwdOpts o; o.X = X; o.target = nullptr; o.labels = Y; o.B = B; o.noise = use_noise != 0; o.keep = keep;
@@ -1110,7 +1117,7 @@ int do_cls(mmae_engine* e, const float* X, const float* Y, int64_t B, int use_no
   r = e->sums_allreduce(); if (r) return r;
   r = e->backward_cls(B, keep); if (r) return r;
   e->last_B = B;
-  return e->advance_step();
+  return e->advance_step(!defer_advance);
 }
 
 // stage a host batch into the double-buffered device input; returns the device pointers
@@ -1385,16 +1392,16 @@ int mmae_apply_update(mmae_engine* e, int optimizer) {
 
 namespace {
 int train_core(mmae_engine* e, const float* Xd, const float* target, int64_t batch, int use_noise, float keep) {
-  int r = do_train(e, Xd, batch, use_noise, keep, target); if (r) return r;
+  int r = do_train(e, Xd, batch, use_noise, keep, target, true); if (r) return r;
   r = e->allreduce_grads(); if (r) return r;
-  r = e->finalize_scalars(batch, true, false); if (r) return r;
-  return e->apply_update(0, batch);
+  r = e->finalize_scalars(batch, true, false, 0, true); if (r) return r;
+  return e->apply_update(0, batch, true);
 }
 int cls_core(mmae_engine* e, const float* Xd, const float* Yd, int64_t batch, int use_noise, float keep) {
-  int r = do_cls(e, Xd, Yd, batch, use_noise, keep); if (r) return r;
+  int r = do_cls(e, Xd, Yd, batch, use_noise, keep, true); if (r) return r;
   r = e->allreduce_grads(); if (r) return r;
-  r = e->finalize_scalars(batch, false, true); if (r) return r;
-  return e->apply_update(1, batch);
+  r = e->finalize_scalars(batch, false, true, 1, true); if (r) return r;
+  return e->apply_update(1, batch, true);
 }
 mmae_engine::GraphKey graph_key(mmae_engine* e, int kind, const void* X, const void* Y, const void* T, int64_t B, int noise, float keep) {
   mmae_engine::GraphKey k; memset(&k, 0, sizeof(k));

@@ -412,8 +412,11 @@ __global__ void pack_sums_kernel(double* sums, float* tail, int to_tail) {
   int i = threadIdx.x;
   if (i < 8) { if (to_tail) tail[i] = (float)sums[i]; else sums[i] = (double)tail[i]; }
 }
+struct StepState;
 struct FinalizeArgs {
   const double* sums; double* scalars; int loss; int variational; double n_elems, batch, head_count; int do_recon, do_head;
+  // end-of-step bookkeeping folded into this single-thread kernel (small-batch steps are launch-latency bound):
+  StepState* state; int prep_opt; double lr, b1, b2; int advance;      // prep_opt >= 0: ++t, alpha for that optimizer; advance: ++step
 };
 __global__ void finalize_scalars_kernel(FinalizeArgs a) {
   if (a.do_recon) {
@@ -424,6 +427,13 @@ __global__ void finalize_scalars_kernel(FinalizeArgs a) {
   if (a.do_head) {
     a.scalars[MMAE_S_HEAD_LOSS] = a.sums[2] / a.head_count;
     a.scalars[MMAE_S_HEAD_ACC] = a.sums[3] / a.head_count;
+  }
+  if (a.state) {
+    if (a.prep_opt >= 0) {
+      const long long t = ++a.state->t[a.prep_opt];
+      a.state->alpha[a.prep_opt] = (float)(a.lr * sqrt(1.0 - pow(a.b2, (double)t)) / (1.0 - pow(a.b1, (double)t)));
+    }
+    if (a.advance) a.state->step += 1u;
   }
 }
 
