@@ -17,7 +17,10 @@ STARTS, NAMES = [0, 200, 220, 240, 270, 320], ['phys', 'call', 'sms', 'screen', 
 ok = True
 for name, kw in (('rmse-dropout', dict(loss_func='mean_squared', tie_weights=True)),
                  ('vae', dict(variational=True, tie_weights=False, layer_sizes=[128, 64, 32])),
-                 ('sce-untied-tf32', dict(tie_weights=False, precision='tf32'))):
+                 ('sce-untied-tf32', dict(tie_weights=False, precision='tf32')),
+                 # wide first layer: its weight gradient is all-reduced in four row blocks while it is still being computed
+                 ('wide-first-layer-tf32', dict(tie_weights=False, precision='tf32', num_feats=1024, layer_sizes=[4096, 64],
+                                                modality_starts=[0, 256, 512, 640, 768, 1024]))):
     base = dict(num_feats=320, layer_sizes=[128, 64], modality_starts=STARTS, modality_names=NAMES, weight_penalty=0.001,
                 learning_rate=1e-3, seed=5, precision='fp32')
     base.update(kw)
@@ -30,7 +33,7 @@ for name, kw in (('rmse-dropout', dict(loss_func='mean_squared', tie_weights=Tru
         params[vname] = np.full(shp, 0.1, np.float32) if len(shp) == 1 else (rng.standard_normal(shp) / np.sqrt(shp[0])).astype(np.float32)
     eng.set_params(params)
     first, rows = dp.attach_data_parallel(eng, Bg, dist)
-    X = rng.uniform(0, 1, (Bg, 320)).astype(np.float32)
+    X = rng.uniform(0, 1, (Bg, cfg.num_feats)).astype(np.float32)
     keep = 0.5 if 'dropout' in name else 1.0
     losses = []
     for s in range(3):
