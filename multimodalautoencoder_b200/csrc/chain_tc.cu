@@ -589,7 +589,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
 }
 
 cudaError_t chain_launch(const ChainParams& p, int grid, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured_dev[64] = {};        // the attribute is per device: one flag per device ordinal
+  int dev_ = 0; cudaGetDevice(&dev_);
+  bool& configured = configured_dev[dev_ & 63];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
     if (e != cudaSuccess) return e;

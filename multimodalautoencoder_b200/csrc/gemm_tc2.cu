@@ -343,7 +343,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NOISE ? TC2_THREADS_
 
 template <bool A_MN, bool B_MN, bool NOISE>
 static cudaError_t tc2_launch_inst(const TcParams& p, int grid, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured_dev[64] = {};        // the attribute is per device: one flag per device ordinal
+  int dev_ = 0; cudaGetDevice(&dev_);
+  bool& configured = configured_dev[dev_ & 63];
   auto kern = gemm_tc2_kernel<A_MN, B_MN, NOISE>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM);

@@ -409,7 +409,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
 template <int BN, bool A_MN, bool B_MN>
 inline cudaError_t tc_launch_inst(const TcParams& p, int grid, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured_dev[64] = {};        // the attribute is per device: one flag per device ordinal
+  int dev_ = 0; cudaGetDevice(&dev_);
+  bool& configured = configured_dev[dev_ & 63];
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes);
