@@ -21,7 +21,7 @@ struct GemmArgs {
   const float* B; int64_t ldb;
   float* C; int64_t ldc;
   NoiseView noise;      // applied to A's stored (row, col) = (batch row, feature) when enabled
-  int noise_aligned32 = 0;   // modality boundaries are multiples of 32 columns (two-SM tcgen05 patch fast path)
+  int noise_aligned32;       // modality boundaries are multiples of 32 columns (two-SM tcgen05 patch fast path)
   Epilogue ep;
   int splits;           // split-K over blockIdx.z: the CTAs of one output tile write their partial tiles to `ws`, the last one
   int64_t k_per_split;  //   to arrive (per-tile counter) adds them up in slice order and runs the epilogue: one launch,
