@@ -1,12 +1,20 @@
 """fp64 NumPy ORACLE for the MMAE hot path.  TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
 
-PARITY UNPINNED: the reference (natashamjaques/MultimodalAutoencoder) ships no
-tests, fixtures or golden vectors, is Python-2 source and computes in TensorFlow
-1.x, which is neither installed here nor installable (no network).  This file is
-therefore a CPU *restatement* of the reference's graph, written from the
-reference source and from the published TF-1.x op semantics listed below; it was
-never checked against a running TensorFlow.  It is cross-checked instead against
-an independent torch.autograd fp64 derivation (tests/test_oracle_autograd.py).
+PINNING: the reference ships no tests, fixtures or golden vectors and computes in
+TensorFlow 1.x, which is neither installed here nor installable (no network).  The
+reference's OWN Python is run instead: `oracle/build_ref.py` converts its Python-2
+source mechanically to Python 3 (`oracle/_ref/`, git-ignored build product) and
+`oracle/tf1_shim` supplies the ~45 TF-1 API names it calls on top of torch autograd.
+`tests/test_oracle_vs_ref.py` checks this file against that run -- the reference's
+build_graph / encode / decode / classify / add_noise_to_batch / train /
+train_classification / predict / per-modality RMSE and its DataLoader's sampling and
+missing-block rule -- to 1e-9 (noise, indices, predictions: bit-exact), and
+`tests/golden/make_golden.py` stores the reference-run values in every golden file.
+What remains restated rather than executed: the TF op KERNELS themselves (items 1-9
+below, implemented in the shim from the published TF-1.x semantics); the graph wiring,
+variable sets per optimizer, RNG call order and host logic are the reference's code.
+It is also cross-checked against an independent torch.autograd fp64 derivation
+(tests/test_oracle_autograd.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this module.  The product path
