@@ -102,8 +102,10 @@ struct mmae_engine {
   int64_t cap = 0;
   uint32_t *zero_bits = nullptr, *mod_bits = nullptr, *miss_bits = nullptr;
   int64_t noise_rows = 0;
-  float* xin[2] = {nullptr, nullptr};             // host-fed / gathered batches (double buffered)
+  float* xin[2] = {nullptr, nullptr};             // host-fed batches (double buffered, filled on copy_stream)
   float* yin[2] = {nullptr, nullptr};
+  float *gxb = nullptr, *gyb = nullptr;           // batches gathered from a resident dataset (engine stream only: never
+  int64_t cap_res = 0;                            // shared with the host staging above, whose copies run on copy_stream)
   cudaEvent_t xin_free[2] = {nullptr, nullptr}, xin_ready[2] = {nullptr, nullptr};
   int xin_turn = 0;
   float* noisy = nullptr;
@@ -395,6 +397,17 @@ struct mmae_engine {
     return 0;
   }
 
+  int ensure_resident(int64_t B) {
+    RET(ensure_cap(B));
+    if (B <= cap_res) return 0;
+    CK(cudaStreamSynchronize(stream));
+    clear_graphs();
+    int64_t nc = std::max<int64_t>(B, cap_res + cap_res / 2);
+    RET(realloc_dev(gxb, nc * F)); RET(realloc_dev(gyb, nc * std::max(C, 1)));
+    cap_res = nc;
+    return 0;
+  }
+
   int* tile_counters = nullptr; int64_t counters_cap = 0;
   int ensure_counters(int64_t count) {
     if (count <= counters_cap) return 0;
@@ -419,7 +432,7 @@ struct mmae_engine {
     fr(d_state); fr(PT); fr(colpart); fr(P); fr(G); fr(M0); fr(V0); fr(M1); fr(V1); fr(d_scalars); fr(d_sums); fr(d_segs[0]); fr(d_segs[1]);
     fr(d_col_mod); fr(d_starts); fr(zero_bits); fr(mod_bits); fr(miss_bits);
     for (int i = 0; i < 2; ++i) { fr(xin[i]); fr(yin[i]); fr(ds_X[i]); fr(ds_Y[i]); }
-    fr(noisy);
+    fr(noisy); fr(gxb); fr(gyb);
     for (auto p : ea) fr(p); for (auto p : da) fr(p); for (auto p : ha) fr(p);
     fr(mu); fr(lv); fr(eps); fr(emb); fr(glv); fr(out); fr(dA); fr(dB);
     fr(hlogits); fr(hdelta); fr(hprobs); fr(hpreds); fr(partials); fr(colsum_ws); fr(splitk_ws); fr(tile_counters); fr(d_idx);
@@ -1599,8 +1612,11 @@ int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, 
   if (slot < 0 || slot > 1 || !e->ds_X[slot]) return e->fail(MMAE_ERR_STATE, "dataset slot is empty");
   if (classification && !e->ds_Y[slot]) return e->fail(MMAE_ERR_STATE, "dataset slot has no labels");
   if (classification && e->H == 0) return e->fail(MMAE_ERR_STATE, "engine was created without a classification head");
-  int r = e->ensure_host(batch); if (r) return r;
-  r = e->ensure_cap(batch); if (r) return r;
+  if (classification) {
+    const int want_cols = e->cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? e->C : 1;
+    if (e->ds_ycols[slot] != want_cols) return e->fail(MMAE_ERR_INVALID, "dataset label columns do not match the head (need C for a sigmoid head, 1 for softmax)");
+  }
+  int r = e->ensure_resident(batch); if (r) return r;
   // device-side sampling (Philox row indices, gather, Philox noise) + the optimizer step: every per-step value comes
   // from StepState in device memory, so the whole sequence replays as one graph
   auto body = [&]() -> int {
@@ -1614,17 +1630,17 @@ int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, 
       ++e->launches;
     }
     const int wpb = 8;
-    gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_X[slot], e->d_idx, e->xin[0], batch, e->F);
+    gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_X[slot], e->d_idx, e->gxb, batch, e->F);
     ++e->launches;
     if (classification) {
-      gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_Y[slot], e->d_idx, e->yin[0], batch, e->ds_ycols[slot]);
+      gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_Y[slot], e->d_idx, e->gyb, batch, e->ds_ycols[slot]);
       ++e->launches;
     }
     ce = cudaGetLastError();
     if (ce != cudaSuccess) return e->cuda_fail(ce, "gather");
     if (gen_noise) { int rr = launch_noise_gen(e, batch, e->first_row); if (rr) return rr; }
-    return classification ? cls_core(e, e->xin[0], e->yin[0], batch, gen_noise ? 1 : 0, keep)
-                          : train_core(e, e->xin[0], nullptr, batch, gen_noise ? 1 : 0, keep);
+    return classification ? cls_core(e, e->gxb, e->gyb, batch, gen_noise ? 1 : 0, keep)
+                          : train_core(e, e->gxb, nullptr, batch, gen_noise ? 1 : 0, keep);
   };
   if (idx_host || e->sticky) return body();            // host-supplied indices: pageable copy, stay eager
   return e->run_graphed(graph_key(e, 2 + slot * 2 + (classification ? 1 : 0), e->ds_X[slot], e->ds_Y[slot], nullptr, batch, gen_noise ? 1 : 0, keep),

@@ -290,7 +290,7 @@ __global__ void head_loss_kernel(const HeadLossArgs a) {
       if (a.probs) for (int c = 0; c < a.C; ++c) a.probs[r * a.C + c] = sigmoidf_(l[c]);
       if (a.preds) a.preds[r] = am;                    // argmax (:450)
       if (a.labels) {
-        int y = (int)a.labels[r];
+        int y = min(max((int)a.labels[r], 0), a.C - 1);   // the Python layer rejects out-of-range labels; never index past the row
         ls += mx + logf(se) - l[y];
         correct += (am == y) ? 1.f : 0.f;
         if (a.delta) for (int c = 0; c < a.C; ++c)

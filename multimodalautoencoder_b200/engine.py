@@ -149,6 +149,25 @@ class Engine:
             t = t.to(device=self.device, dtype=dtype or torch.float32).contiguous()
         return t
 
+    def _check_labels(self, Y, B):
+        """The head reads B*C floats for a sigmoid head and B class indices for a softmax head (TensorFlow raises a
+        shape error for anything else; here a wrong shape would be an out-of-bounds device read)."""
+        heads = self.cfg.head_widths()
+        if not heads:
+            raise ValueError('engine was created without a classification head')
+        Cn = heads[-1]
+        n = int(np.prod(tuple(Y.shape) if hasattr(Y, 'shape') else np.shape(Y)))
+        if self.cfg.cls_loss == 'sigmoid_cross_entropy':
+            if n != B * Cn:
+                raise ValueError('labels have %d values, the sigmoid head needs [%d, %d]' % (n, B, Cn))
+        else:
+            if n != B:
+                raise ValueError('labels have %d values, the softmax head needs one class index per row (%d)' % (n, B))
+            if not isinstance(Y, self._torch.Tensor):
+                yi = np.asarray(Y)
+                if yi.size and (yi.min() < 0 or yi.max() >= Cn):
+                    raise ValueError('class indices must lie in [0, %d)' % Cn)
+
     # ------------------------------------------------------------------ variables
     def variables(self):
         if self._names is None:
@@ -237,6 +256,8 @@ class Engine:
         X = self._dev(X)
         B = X.shape[0]
         tgt = None if target is None else self._dev(target)
+        if labels is not None:
+            self._check_labels(labels, B)
         lab = None if labels is None else self._dev(labels)
         want = 0
         o = capi.Outputs()
@@ -306,6 +327,7 @@ class Engine:
 
     def cls_train_step(self, X, Y, noise=False, keep=1.0):
         X = self._dev(X)
+        self._check_labels(Y, X.shape[0])
         Y = self._dev(Y)
         self._ck(self.lib.mmae_cls_train_step(self._h, C.c_void_p(X.data_ptr()), C.c_void_p(Y.data_ptr()),
                                               X.shape[0], int(bool(noise)), float(keep)))
@@ -318,6 +340,7 @@ class Engine:
 
     def cls_train_step_host(self, X_host, Y_host, gen_noise=False, keep=1.0, use_noise=False):
         ptr, B = self._host_ptr(X_host)
+        self._check_labels(Y_host, B)
         yptr, _ = self._host_ptr(Y_host)
         self._ck(self.lib.mmae_cls_train_step_host(self._h, ptr, yptr, B, 1 if gen_noise else (2 if use_noise else 0), float(keep)))
 
@@ -339,6 +362,8 @@ class Engine:
         B = X.shape[0]
         tgt = None if target_host is None else np.ascontiguousarray(target_host, np.float32)
         lab = None if labels_host is None else np.ascontiguousarray(labels_host, np.float32)
+        if lab is not None:
+            self._check_labels(lab, B)
         o = capi.Outputs()
         res = {}
         want = 0
@@ -391,6 +416,7 @@ class Engine:
         yp = None
         if Y is not None:
             Y = np.ascontiguousarray(Y, np.float32)
+            self._check_labels(Y, X.shape[0])
             yc = 1 if Y.ndim == 1 else Y.shape[1]
             yp = Y.ctypes.data_as(C.c_void_p)
         self._ck(self.lib.mmae_set_dataset(self._h, slot, X.ctypes.data_as(C.c_void_p), yp, X.shape[0], yc))

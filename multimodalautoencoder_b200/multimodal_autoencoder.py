@@ -221,7 +221,10 @@ class MultimodalAutoencoder:
         """Initial values with the reference's distributions (:22-56): 'xavier' U(+-sqrt(6/(in+out))), otherwise
         truncated normal (|z| <= 2) with sigma 1/sqrt(in); biases 0.1.  (TensorFlow's RNG stream itself is not
         reproducible; parity runs inject weights through engine.set_variable.)"""
-        rng = np.random.default_rng(self.seed)
+        # every (re)build draws fresh weights, like a new TensorFlow initializer run: the stream is keyed by the seed AND
+        # by how many times this model has been initialised (CV folds / grid settings do not restart from equal weights)
+        self._init_count = getattr(self, '_init_count', 0) + 1
+        rng = np.random.default_rng([int(self.seed), self._init_count - 1])
         for name, shp in self.engine.variables():
             if len(shp) == 1:
                 w = np.full(shp, 0.1, np.float32)
@@ -331,6 +334,9 @@ class MultimodalAutoencoder:
                 zb, mb = eng.get_noise(len(X))                  # keep the training descriptor for the optimizer step
                 val_loss = self._loss_on(val_X, noise=True)
                 eng.set_noise(zb, mb)
+                # the evaluation forwards advanced the engine's Philox step past the host counter: take a fresh one so
+                # that this optimizer step and the next do not share dropout masks / epsilon
+                eng.set_rng_step(self._next_rng_step())
                 if 'entropy' in self.loss_func:                 # :733-735
                     train_loss, val_loss = train_loss / len(X), val_loss / len(val_X)
                 self.train_loss.append(train_loss)
@@ -398,6 +404,7 @@ class MultimodalAutoencoder:
             self._prepare_noise(len(X))
             if step % self.record_every_nth == 0:
                 res = self.evaluate_classification_performance((X, Y, True, self.classification_dropout_prob))
+                eng.set_rng_step(self._next_rng_step())         # see train(): evaluation forwards advanced the engine's step
                 train_loss, train_acc, val_loss, val_acc = res
                 self.train_acc.append(train_acc)
                 self.val_acc.append(val_acc)
@@ -475,13 +482,17 @@ class MultimodalAutoencoder:
         np.savez(path, train_loss=self.train_loss, val_loss=self.val_loss, layer_sizes=self.layer_sizes,
                  variational=self.variational, dropout_prob=self.dropout_prob, weight_penalty=self.weight_penalty,
                  activation_func=self.activation_func, loss_func=self.loss_func,
-                 weight_initialization=self.weight_initialization, tie_weights=self.tie_weights, **blob)
+                 weight_initialization=self.weight_initialization, tie_weights=self.tie_weights,
+                 rng_step_count=np.int64(self._step_count), **blob)
         return path
 
     def load_saved_model(self, directory=None, checkpoint_name=None, npz_file_name=None):
         """Restores hyper-parameters, weights and optimizer state from a save_model() file."""
         directory = directory or self.checkpoint_dir          # the reference read an undefined self.output_dir (:818)
         name = checkpoint_name or npz_file_name
+        if name is not None and not name.endswith('.npz'):
+            # reference-style names: 'model.ckpt-N' (the TF checkpoint) or 'model-N' (its .npz twin) -> 'model-N.npz'
+            name = name.replace('.ckpt-', '-') + '.npz'
         if name is None:
             cands = sorted((f for f in os.listdir(directory) if f.endswith('.npz')),
                            key=lambda f: os.path.getmtime(os.path.join(directory, f)))
@@ -503,6 +514,8 @@ class MultimodalAutoencoder:
             tl, vl = self.train_loss, self.val_loss
             self.rebuild_reinitialize()
             self.train_loss, self.val_loss = tl, vl
+        if 'rng_step_count' in z.files:                       # a resumed philox run continues its noise / dropout stream
+            self._step_count = int(z['rng_step_count'])
         for name_, _ in self.engine.variables():
             self.engine.set_variable(name_, z['var/' + name_])
             for opt in (0, 1):
@@ -607,9 +620,13 @@ class MultimodalAutoencoder:
         """Reconstructs every row, replaces only the modality blocks that were missing (:1167-1187)."""
         import pandas as pd
         df = pd.read_csv(path + filename, index_col=0)
-        X = df[self.data_loader.wanted_feats].to_numpy()
-        filled = self.fill_missing(X)
-        df.loc[:, self.data_loader.wanted_feats] = filled
+        dl = self.data_loader
+        X = df[dl.wanted_feats].to_numpy(dtype=np.float64)
+        filled = self.fill_missing(X)              # float32, device-side select
+        # only the blocks that were missing are written back: every observed cell keeps its float64 value bit for bit
+        # (fill_df_with_reconstruction touches nothing else, data_funcs.py:328-348); the rule runs on the float64 matrix
+        cols = np.repeat(dl.missing_modality_mask(X), np.diff(dl.modality_start_indices), axis=1)
+        df.loc[:, dl.wanted_feats] = np.where(cols, filled.astype(np.float64), X)
         df.to_csv(path + 'MMAE_filled-' + file_descriptor + filename)
         return df
 

@@ -146,3 +146,72 @@ def test_wrapper_sweeps_a_small_grid(tmp_path):
     c.sweep_all_parameters()
     for col in ('val_loss', 'val_acc', 'val_auc', 'val_f1', 'noisy_val_acc', 'clean_val_auc', 'val_acc_happiness'):
         assert col in c.val_results_df.columns, col
+
+
+def test_predict_right_after_resident_training_is_ordered():
+    """Regression: the philox path gathers its batches into buffers of its own; a host-fed forward issued right after
+    queued resident train steps must neither read training rows nor corrupt the last step's layer-0 weight gradient."""
+    from multimodalautoencoder_b200 import MultimodalAutoencoder
+    _, dl, _ = _loaders()
+    kw = dict(data_loader=dl, layer_sizes=[128, 64], variational=False, tie_weights=True, batch_size=256, learning_rate=1e-3,
+              weight_initialization='normal', verbose=False, precision='fp32', rng_mode='philox', seed=3)
+    X = np.ascontiguousarray(dl.val_X[:200])
+    runs = []
+    for synced in (True, False):
+        m = MultimodalAutoencoder(**kw)
+        m.train(25, record_every_nth=1000, save_every_nth=10 ** 6)
+        if synced:
+            m.engine.synchronize()
+        rec, loss = m.predict(X)                      # batch <= train batch: no workspace growth, no implicit sync
+        runs.append((rec, loss, m.engine.get_params()))
+        m.close()
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]
+    for k in runs[0][2]:
+        assert np.array_equal(runs[0][2][k], runs[1][2][k]), k
+
+
+def test_label_shapes_are_validated():
+    from multimodalautoencoder_b200 import Engine
+    from tests.helpers import make_cfgs
+    _, ecfg = make_cfgs(head=[8], num_labels=None, cls_loss='softmax')
+    e = Engine(ecfg)
+    X = np.random.default_rng(0).uniform(size=(16, 320)).astype(np.float32)
+    with pytest.raises(ValueError):
+        e.cls_train_step(X, np.zeros((16, 2), np.float32))          # softmax head wants [B] class indices
+    with pytest.raises(ValueError):
+        e.cls_train_step(X, np.full(16, 2, np.float32))             # class index out of range
+    e.cls_train_step(X, np.ones(16, np.float32))
+    e.close()
+    _, ecfg = make_cfgs(head=[8], num_labels=3)
+    e = Engine(ecfg)
+    with pytest.raises(ValueError):
+        e.cls_train_step(X, np.zeros(16, np.float32))               # sigmoid head wants [B, 3]
+    with pytest.raises(ValueError):
+        e.set_dataset(1, X, np.zeros(16, np.float32))
+    e.close()
+
+
+def test_rebuild_draws_fresh_weights_and_record_steps_do_not_repeat_dropout(tmp_path):
+    from multimodalautoencoder_b200 import MultimodalAutoencoder
+    _, dl, _ = _loaders(600)
+    m = MultimodalAutoencoder(data_loader=dl, layer_sizes=[32, 8], variational=False, tie_weights=True, batch_size=20,
+                              dropout_prob=0.5, weight_initialization='normal', verbose=False, rng_mode='numpy',
+                              checkpoint_dir=str(tmp_path) + '/')
+    w_a = m.engine.get_variable('weights0')
+    m.rebuild_reinitialize()
+    assert not np.array_equal(w_a, m.engine.get_variable('weights0'))           # a rebuild is a new initializer run
+    np.random.seed(0)
+    m.train(3, record_every_nth=1, save_every_nth=10 ** 6)                        # every step is a record step
+    # host counter and engine step agree after record steps: the next descriptor upload does not rewind the engine
+    steps_before = m._step_count
+    m.train(1, record_every_nth=1000, save_every_nth=10 ** 6)
+    assert m._step_count > steps_before
+    path = m.save_model()
+    m2 = MultimodalAutoencoder(data_loader=dl, layer_sizes=[32, 8], variational=False, tie_weights=True, batch_size=20,
+                               dropout_prob=0.5, weight_initialization='normal', verbose=False, rng_mode='numpy',
+                               checkpoint_dir=str(tmp_path) + '/')
+    ref_style = os.path.basename(path)[:-4].rsplit('-', 1)
+    m2.load_saved_model(directory=str(tmp_path) + '/', checkpoint_name=ref_style[0] + '.ckpt-' + ref_style[1])
+    assert m2._step_count == m._step_count
+    assert np.array_equal(m2.engine.get_variable('weights0'), m.engine.get_variable('weights0'))
+    m.close(); m2.close()
