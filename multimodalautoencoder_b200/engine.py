@@ -154,7 +154,7 @@ class Engine:
         shape error for anything else; here a wrong shape would be an out-of-bounds device read)."""
         heads = self.cfg.head_widths()
         if not heads:
-            raise ValueError('engine was created without a classification head')
+            return                      # the C call reports the missing head (MMAE_ERR_STATE -> EngineError)
         Cn = heads[-1]
         n = int(np.prod(tuple(Y.shape) if hasattr(Y, 'shape') else np.shape(Y)))
         if self.cfg.cls_loss == 'sigmoid_cross_entropy':
