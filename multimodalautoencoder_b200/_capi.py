@@ -82,6 +82,7 @@ PROTOTYPES = {
     'mmae_set_shard': (_I, [_P, _L, _L]),
     'mmae_kernel_launches': (_L, [_P]),
     'mmae_chain_launches': (_L, [_P]),
+    'mmae_backward_chain_launches': (_L, [_P]),
     'mmae_graph_replays': (_L, [_P]),
     'mmae_fused_noise_launches': (_L, [_P]),
     'mmae_set_profiling': (_I, [_P, _I]),

@@ -172,6 +172,119 @@ __device__ __forceinline__ void chain_act_dispatch(const ChainOp& o, const CUten
   }
 }
 
+// ------------------------------------------------------------------ backward chain: epilogue of a non-final dgrad op
+// v = (delta . W^T) * act'(h) * dropmask/keep with h the saved forward activation; TMEM <- tf32(v)
+// in place (the next dgrad op's A operand), global copy of delta for the weight-gradient GEMMs through the swizzled
+// tile + TMA store, per-32-row column sums (bias gradient) read back column-wise from the same tile.
+// The saved activations are read straight from global memory (thread = row, 8 x 16 B): the loads are issued before the
+// accumulator is awaited, so their latency hides behind the MMAs of this op.
+struct DgradAux { float4 v[8]; };
+__device__ __forceinline__ void chain_dgrad_load_aux(const ChainOp& o, int col0, int64_t row, int64_t M, DgradAux& ax) {
+  const bool row_ok = row < M && o.ep.saved != nullptr;
+  const float* sp = o.ep.saved + row * o.ep.lds + col0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const bool ok = row_ok && (col0 + q * 4 + 3 < o.N);
+    if (ok) asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(ax.v[q].x), "=f"(ax.v[q].y), "=f"(ax.v[q].z), "=f"(ax.v[q].w) : "l"(sp + q * 4));
+    else ax.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int ACT, bool DROP>
+__device__ __forceinline__ void chain_dgrad_chunk(const ChainOp& o, const CUtensorMap* tmO, uint32_t taddr, int col0, int64_t tile_row0,
+                                                  int64_t M, int quad, int lane, const DgradAux& ax, EpiStage& es) {
+  uint32_t r[32];
+  tc_ld32(taddr, r);
+  const uint32_t tile = smem_u32(es.buf[0]);
+  if (o.has_out) {
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+  }
+  const int64_t lrow = tile_row0 + quad * 32 + lane;
+  const int64_t grow = lrow + o.ep.row0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float hs[4] = {ax.v[q].x, ax.v[q].y, ax.v[q].z, ax.v[q].w};
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float g = __uint_as_float(r[q * 4 + e]);
+      float h = hs[e];
+      if (DROP) {
+        uint32_t w = philox_word((uint64_t)grow * (uint64_t)o.ep.drop_width + (uint64_t)(col0 + q * 4 + e), o.ep.drop_stream, __ldg(o.ep.step), o.ep.seed);
+        if ((w >> 8) < o.ep.keep_thr) { g = g / o.ep.keep; h = h * o.ep.keep; } else { g = 0.f; }
+      }
+      v[e] = g * dact_t<ACT>(h);
+      r[q * 4 + e] = to_tf32(v[e]);
+    }
+    if (o.has_out) sts128(row_chunk(tile, lane, q), make_float4(v[0], v[1], v[2], v[3]));
+  }
+  tc_st32(taddr, r);
+  if (o.has_out) {
+    __syncwarp();
+    if (o.ep.colsum_partials) {
+      const int col = col0 + lane;
+      const int64_t row0 = tile_row0 + quad * 32;
+      if (row0 < M) {
+        float cs = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr)        // rows past M hold exact zeros (zero-filled operands, zero aux)
+          cs += lds32(tile + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4);
+        if (col < o.N) o.ep.colsum_partials[(row0 >> 5) * o.N + col] = cs;
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) { tma_store_2d(tmO, es.buf[0], col0, (int)(tile_row0 + quad * 32)); bulk_commit(); }
+    es.uses++;
+  }
+}
+template <bool DROP>
+__device__ __forceinline__ void chain_dgrad_dispatch(const ChainOp& o, const CUtensorMap* tmO, uint32_t taddr, int col0, int64_t tile_row0,
+                                                     int64_t M, int quad, int lane, const DgradAux& ax, EpiStage& es) {
+  switch (o.ep.act) {
+    case MMAE_ACT_RELU: chain_dgrad_chunk<MMAE_ACT_RELU, DROP>(o, tmO, taddr, col0, tile_row0, M, quad, lane, ax, es); break;
+    case MMAE_ACT_TANH: chain_dgrad_chunk<MMAE_ACT_TANH, DROP>(o, tmO, taddr, col0, tile_row0, M, quad, lane, ax, es); break;
+    case MMAE_ACT_SOFTSIGN: chain_dgrad_chunk<MMAE_ACT_SOFTSIGN, DROP>(o, tmO, taddr, col0, tile_row0, M, quad, lane, ax, es); break;
+    case MMAE_ACT_SOFTPLUS: chain_dgrad_chunk<MMAE_ACT_SOFTPLUS, DROP>(o, tmO, taddr, col0, tile_row0, M, quad, lane, ax, es); break;
+    default: chain_dgrad_chunk<MMAE_ACT_LINEAR, DROP>(o, tmO, taddr, col0, tile_row0, M, quad, lane, ax, es); break;
+  }
+}
+
+// final dgrad op: the saved activation tile arrives by TMA (like the loss target), the result overwrites it in place
+template <int ACT, bool DROP>
+__device__ __forceinline__ void chain_final_dgrad_chunk(const ChainOp& o, uint32_t taddr, int col0, int64_t grow, int lane, uint32_t tile) {
+  uint32_t r[32];
+  tc_ld32(taddr, r);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 h4 = lds128(row_chunk(tile, lane, q));
+    const float hs[4] = {h4.x, h4.y, h4.z, h4.w};
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float g = __uint_as_float(r[q * 4 + e]);
+      float h = hs[e];
+      if (DROP) {
+        uint32_t w = philox_word((uint64_t)grow * (uint64_t)o.ep.drop_width + (uint64_t)(col0 + q * 4 + e), o.ep.drop_stream, __ldg(o.ep.step), o.ep.seed);
+        if ((w >> 8) < o.ep.keep_thr) { g = g / o.ep.keep; h = h * o.ep.keep; } else { g = 0.f; }
+      }
+      v[e] = g * dact_t<ACT>(h);
+    }
+    sts128(row_chunk(tile, lane, q), make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+template <bool DROP>
+__device__ __forceinline__ void chain_final_dgrad_dispatch(const ChainOp& o, uint32_t taddr, int col0, int64_t grow, int lane, uint32_t tile) {
+  switch (o.ep.act) {
+    case MMAE_ACT_RELU: chain_final_dgrad_chunk<MMAE_ACT_RELU, DROP>(o, taddr, col0, grow, lane, tile); break;
+    case MMAE_ACT_TANH: chain_final_dgrad_chunk<MMAE_ACT_TANH, DROP>(o, taddr, col0, grow, lane, tile); break;
+    case MMAE_ACT_SOFTSIGN: chain_final_dgrad_chunk<MMAE_ACT_SOFTSIGN, DROP>(o, taddr, col0, grow, lane, tile); break;
+    case MMAE_ACT_SOFTPLUS: chain_final_dgrad_chunk<MMAE_ACT_SOFTPLUS, DROP>(o, taddr, col0, grow, lane, tile); break;
+    default: chain_final_dgrad_chunk<MMAE_ACT_LINEAR, DROP>(o, taddr, col0, grow, lane, tile); break;
+  }
+}
+
 // ------------------------------------------------------------------ epilogue of the final op, one 32-column chunk
 // l = acc + bias; loss += f(l, target); out = dLoss/dl (TRAIN) or decoded_X (PRED).  The target tile was loaded by
 // TMA into `tile`; the result overwrites it in place and leaves with a TMA store.  AUX = a target is present.
@@ -247,6 +360,9 @@ __device__ __forceinline__ void chain_final_dispatch(const ChainOp& o, uint32_t 
 }
 
 // ------------------------------------------------------------------ the kernel
+// BWD = false: forward chain (bias + activation epilogues, loss / fill-in in the final op);  BWD = true: backward dgrad
+// chain (act' epilogues).  Two instantiations so that neither carries the other's registers.
+template <bool BWD>
 __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -422,7 +538,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     for (int t = blockIdx.x; t < p.m_tiles; t += gridDim.x, ++it) {
       const uint32_t par = it & 1;
       const int64_t tile_row0 = (int64_t)t * TC_BM;
-      if (p.scan_miss) {
+      if (!BWD && p.scan_miss) {
         // fill-in: missing-block detection (sum == -width, data_funcs.py:366-381) from the X tile while it sits in the
         // ring.  These warps are idle until the first layer's accumulator is complete; warp w owns rows [16w, 16w+16),
         // a lane pair splits the 32 columns of a k-chunk.  Modalities are contiguous, increasing column ranges, so one
@@ -465,13 +581,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
       }
       for (int i = 0; i < last; ++i) {
         const ChainOp& o = p.op[i];
+        DgradAux dax;
+        if (BWD && half < o.n_chunk / 32) chain_dgrad_load_aux(o, half * 32, tile_row0 + quad * 32 + lane, p.M, dax);
         mbar_wait_parked(&mma_done[i], par);
         tc_fence_after();
         if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 2] = clock64();
         const int chunks = o.n_chunk / 32;
         const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)o.d_col;
         for (int ch = half; ch < chunks; ch += 2) {
-          if (o.ep.keep < 1.f) chain_act_dispatch<true>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, quad, lane, smem_u32(bias_s + o.bias_off), es);
+          if (BWD) {
+            if (ch != half) chain_dgrad_load_aux(o, ch * 32, tile_row0 + quad * 32 + lane, p.M, dax);     // (the first chunk's loads were issued before the wait)
+            if (o.ep.keep < 1.f) chain_dgrad_dispatch<true>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, p.M, quad, lane, dax, es);
+            else chain_dgrad_dispatch<false>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, p.M, quad, lane, dax, es);
+          } else if (o.ep.keep < 1.f) chain_act_dispatch<true>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, quad, lane, smem_u32(bias_s + o.bias_off), es);
           else chain_act_dispatch<false>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, quad, lane, smem_u32(bias_s + o.bias_off), es);
           tc_wait_st();
           tc_fence_before();
@@ -517,8 +639,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
       if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + last) * 4 + 2] = clock64();
       const bool row_valid = (int64_t)row0 + lane < p.M;
       uint32_t miss = 0u;
-      if (p.scan_miss) { mbar_wait_parked(&miss_ready[it & 1], (it >> 1) & 1); miss = miss_s[(it & 1) * 128 + quad * 32 + lane]; }
-      else if (lo.ep.fill_bits && row_valid) miss = __ldg(lo.ep.fill_bits + row0 + lane);
+      if (!BWD && p.scan_miss) { mbar_wait_parked(&miss_ready[it & 1], (it >> 1) & 1); miss = miss_s[(it & 1) * 128 + quad * 32 + lane]; }
+      else if (!BWD && lo.ep.fill_bits && row_valid) miss = __ldg(lo.ep.fill_bits + row0 + lane);
       for (int ch = half; ch < lchunks; ch += 2) {
         if (ch * 32 >= lo.N) break;                                   // padding columns only
         const int b = es.uses & 1;
@@ -537,7 +659,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
         if (has_aux) { mbar_wait_parked(es.aux_bar[b], es.aux_phase[b]); es.aux_phase[b] ^= 1; }
         uint8_t* tile_p = es.buf[b];
         const uint32_t tile = smem_u32(tile_p);
-        if (lo.ep.mode == EPI_LOSS_TRAIN) {
+        if (BWD) {
+          const int64_t grow = (int64_t)row0 + lane + lo.ep.row0;
+          if (lo.ep.keep < 1.f) chain_final_dgrad_dispatch<true>(lo, tbase + ch * 32, ch * 32, grow, lane, tile);
+          else chain_final_dgrad_dispatch<false>(lo, tbase + ch * 32, ch * 32, grow, lane, tile);
+        } else if (lo.ep.mode == EPI_LOSS_TRAIN) {
           if (has_aux) chain_final_dispatch<EPI_LOSS_TRAIN, true>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc);
           else chain_final_dispatch<EPI_LOSS_TRAIN, false>(lo, tbase + ch * 32, ch * 32, row_valid, lane, lbias, tile, loss_acc);
         } else if (lo.ep.fill_bits && has_aux) {
@@ -593,11 +719,13 @@ cudaError_t chain_launch(const ChainParams& p, int grid, cudaStream_t st) {
   int dev_ = 0; cudaGetDevice(&dev_);
   bool& configured = configured_dev[dev_ & 63];
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  chain_tc_kernel<<<grid, CH_THREADS, CH_SMEM, st>>>(p);
+  if (p.op[0].ep.mode == EPI_DGRAD) chain_tc_kernel<true><<<grid, CH_THREADS, CH_SMEM, st>>>(p);
+  else chain_tc_kernel<false><<<grid, CH_THREADS, CH_SMEM, st>>>(p);
   return cudaGetLastError();
 }
 

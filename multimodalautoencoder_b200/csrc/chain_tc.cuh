@@ -146,8 +146,14 @@ inline bool chain_build(ChainParams& p, const float* X, int64_t M, int64_t ldx, 
     o.d_col = is_last ? 0 : ((i & 1) ? col_r1 : col_r0);
     o.a_col = i > 0 ? p.op[i - 1].d_col : 0;
     o.writeback = is_last ? 0 : 1;
-    if (o.writeback && l.ep.mode != EPI_BIAS_ACT) return false;
-    if (is_last && l.ep.mode != EPI_LOSS_TRAIN && l.ep.mode != EPI_LOSS_PRED) return false;
+    if (o.writeback && l.ep.mode != EPI_BIAS_ACT && l.ep.mode != EPI_DGRAD) return false;
+    if (is_last && l.ep.mode != EPI_LOSS_TRAIN && l.ep.mode != EPI_LOSS_PRED && l.ep.mode != EPI_DGRAD) return false;
+    if ((l.ep.mode == EPI_DGRAD) != (layers[0].ep.mode == EPI_DGRAD)) return false;      // one direction per launch
+    if (l.ep.mode == EPI_DGRAD) {        // backward chain: the saved activation is the auxiliary operand of the epilogue
+      if (l.ep.beta != 0.f || (l.N & 3)) return false;
+      if (l.ep.saved && ((l.ep.lds & 3) || !al(l.ep.saved))) return false;
+      if (is_last && (!l.ep.saved || l.ep.target != l.ep.saved || l.ep.ldt != l.ep.lds)) return false;   // final op: aux tile by TMA
+    }
     o.bias_off = bias_off; bias_off += o.n_chunk * o.n_chunks;
     o.has_out = l.out ? 1 : 0; o.ep = l.ep;
     max_chunk = std::max(max_chunk, o.n_chunk);

@@ -113,6 +113,8 @@ struct mmae_engine {
   float *mu = nullptr, *lv = nullptr, *eps = nullptr, *emb = nullptr, *glv = nullptr;
   float* out = nullptr;                           // [cap, F]: delta_L in training, decoded_X otherwise
   float *dA = nullptr, *dB = nullptr;             // delta ping-pong [cap, maxw]
+  std::vector<float*> dch, cpch;                  // backward chain: delta of every dgrad op [cap, N_k] + its per-32-row column sums
+  int64_t cap_bch = 0;
   float *hlogits = nullptr, *hdelta = nullptr, *hprobs = nullptr;
   int32_t* hpreds = nullptr;
   float* partials = nullptr; int64_t partials_cap = 0;
@@ -127,7 +129,7 @@ struct mmae_engine {
   // ---- CUDA graphs of the train steps (small batches are launch-bound: ~60 launches per step)
   struct GraphKey { int kind; const void* X; const void* Y; const void* T; int64_t B; int noise; float keep; int64_t gb, fr; void* stream;
     bool operator==(const GraphKey& o) const { return kind == o.kind && X == o.X && Y == o.Y && T == o.T && B == o.B && noise == o.noise && keep == o.keep && gb == o.gb && fr == o.fr && stream == o.stream; } };
-  struct GraphEntry { GraphKey key; int seen = 0; cudaGraphExec_t exec = nullptr; int64_t n_launches = 0, n_chain = 0; int opt = 0;
+  struct GraphEntry { GraphKey key; int seen = 0; cudaGraphExec_t exec = nullptr; int64_t n_launches = 0, n_chain = 0, n_bchain = 0; int opt = 0;
     std::vector<char> dirty_after; bool d_fused_after = false, last_tc_after = false; };
   std::vector<GraphEntry> graphs;
   cudaStream_t gstream = nullptr;   // graphs cannot be captured on the legacy default stream: a blocking stream of our own
@@ -408,6 +410,24 @@ struct mmae_engine {
     return 0;
   }
 
+  // width of the delta produced by dgrad op k of the backward chain (see backward_chain)
+  int bch_width(int k) const { return k < L ? layers[k] : layers[2 * L - 2 - k]; }
+  int ensure_bchain(int64_t B) {
+    RET(ensure_acts(B));
+    if (B <= cap_bch) return 0;
+    CK(cudaStreamSynchronize(stream));
+    clear_graphs();
+    const int nops = 2 * L - 1;
+    dch.resize(nops, nullptr); cpch.resize(nops, nullptr);
+    int64_t nc = std::max<int64_t>(B, cap_bch + cap_bch / 2);
+    for (int k = 0; k < nops; ++k) {
+      RET(realloc_dev(dch[k], nc * bch_width(k)));
+      RET(realloc_dev(cpch[k], ((nc + 31) / 32) * (int64_t)bch_width(k)));
+    }
+    cap_bch = nc;
+    return 0;
+  }
+
   int* tile_counters = nullptr; int64_t counters_cap = 0;
   int ensure_counters(int64_t count) {
     if (count <= counters_cap) return 0;
@@ -433,6 +453,7 @@ struct mmae_engine {
     fr(d_col_mod); fr(d_starts); fr(zero_bits); fr(mod_bits); fr(miss_bits);
     for (int i = 0; i < 2; ++i) { fr(xin[i]); fr(yin[i]); fr(ds_X[i]); fr(ds_Y[i]); }
     fr(noisy); fr(gxb); fr(gyb);
+    for (auto q : dch) fr(q); for (auto q : cpch) fr(q);
     for (auto p : ea) fr(p); for (auto p : da) fr(p); for (auto p : ha) fr(p);
     fr(mu); fr(lv); fr(eps); fr(emb); fr(glv); fr(out); fr(dA); fr(dB);
     fr(hlogits); fr(hdelta); fr(hprobs); fr(hpreds); fr(partials); fr(colsum_ws); fr(splitk_ws); fr(tile_counters); fr(d_idx);
@@ -570,8 +591,8 @@ struct mmae_engine {
 
   // db = column sums of delta [rows, n].  `fused` says the GEMM that produced delta already left per-32-row
   // partial sums in colpart (tcgen05 epilogue), so only ceil(rows/32) partial rows are read instead of delta.
-  int bias_grad(const float* D, int64_t rows, int n, int64_t ld, float* outp, bool fused) {
-    if (fused) return colsum(colpart, (rows + 31) / 32, n, n, outp);
+  int bias_grad(const float* D, int64_t rows, int n, int64_t ld, float* outp, bool fused, const float* part = nullptr) {
+    if (fused) return colsum(part ? part : colpart, (rows + 31) / 32, n, n, outp);
     return colsum(D, rows, n, ld, outp);
   }
 
@@ -644,7 +665,7 @@ struct mmae_engine {
     if (!stream && !gstream) CK(cudaStreamCreate(&gstream));
     cudaStream_t cs = stream ? stream : gstream;
     if (ge->exec) {                                              // replay + the host-side effects of one step
-      rng_step += 1; t_opt[ge->opt] += 1; launches += ge->n_launches; chain_launches += ge->n_chain; last_B = B;
+      rng_step += 1; t_opt[ge->opt] += 1; launches += ge->n_launches; chain_launches += ge->n_chain; bchain_launches += ge->n_bchain; last_B = B;
       pt_dirty = ge->dirty_after; d_fused = ge->d_fused_after; last_gemm_tc = ge->last_tc_after;
       ++graph_replays;
       CK(cudaGraphLaunch(ge->exec, cs));
@@ -653,7 +674,7 @@ struct mmae_engine {
     // capture.  All K-major weight shadows are forced stale so that the graph always refreshes the ones it reads.
     const size_t idx = (size_t)(ge - graphs.data());
     std::fill(pt_dirty.begin(), pt_dirty.end(), 1);
-    const int64_t l0 = launches, c0 = chain_launches, cap0 = cap, capa0 = cap_acts, caph0 = cap_host, sk0 = splitk_cap;
+    const int64_t l0 = launches, c0 = chain_launches, bc0 = bchain_launches, cap0 = cap, capa0 = cap_acts, caph0 = cap_host, sk0 = splitk_cap;
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
     if (ce != cudaSuccess) { (void)cudaGetLastError(); graph_mode = 0; return body(); }
@@ -673,7 +694,7 @@ struct mmae_engine {
     ce = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { g.exec = nullptr; graph_mode = 0; return cuda_fail(ce, "cudaGraphInstantiate"); }
-    g.n_launches = launches - l0; g.n_chain = chain_launches - c0;
+    g.n_launches = launches - l0; g.n_chain = chain_launches - c0; g.n_bchain = bchain_launches - bc0;
     g.dirty_after = pt_dirty; g.d_fused_after = d_fused; g.last_tc_after = last_gemm_tc;
     CK(cudaGraphLaunch(g.exec, cs));
     return 0;
@@ -926,8 +947,98 @@ struct mmae_engine {
   }
   bool cls_pass = false;
 
+  // Backward dgrad chain (chain_tc.cuh): every delta of the step in ONE launch, deltas resident in TMEM from layer to
+  // layer.  Op k = 0..L-1 goes down the decoder (delta . D_j^T, j = L-1-k, times act'(da[j-1]); the last of them is
+  // the plain g_e = dL/d(embedding)), op k = L..2L-2 down the encoder (delta . W_i^T, i = 2L-1-k, times act'(ea[i-1])).
+  // Returns 1 when it ran (deltas in dch[k], bias-gradient partials in cpch[k]), 0 when the configuration does not fit.
+  int64_t bchain_launches = 0;
+  int backward_chain(int64_t B, float keep) {
+    if (chain_mode < 0) { const char* ev = getenv("MMAE_CHAIN"); chain_mode = (ev && ev[0] == '0') ? 0 : 1; }
+    static const bool bwd_off = getenv("MMAE_CHAIN_BWD") && getenv("MMAE_CHAIN_BWD")[0] == '0';
+    if (!chain_mode || bwd_off || cfg.precision != MMAE_PREC_TF32 || cfg.variational || B < 32 || L < 2 || !d_fused) return 0;
+    RET(ensure_bchain(B));
+    const int nops = 2 * L - 1;
+    std::vector<ChainLayer> ls;
+    double flops = 0.0;
+    for (int k = 0; k < nops; ++k) {
+      ChainLayer l; memset(&l, 0, sizeof(l));
+      l.ep = epi(EPI_DGRAD); l.ep.act = MMAE_ACT_LINEAR;
+      char wn[32];
+      if (k < L) {                       // decoder layer j = L-1-k, encoder index i = k
+        const int j = L - 1 - k;
+        l.K = enc_in(k); l.N = layers[k]; l.ldw = l.K;
+        if (cfg.tie_weights) { snprintf(wn, 32, "weights%d", k); l.Wkm = shadowT(pvar(wn), l.K, l.N); }     // D_j = W_k^T: K-major [N, K] = shadow of W_k
+        else { snprintf(wn, 32, "decode_weights%d", k); l.Wkm = pvar(wn); }                                  // D_j stored [N, K] already
+        if (j > 0) {
+          l.ep.saved = da[j - 1]; l.ep.lds = l.N; l.ep.act = cfg.activation;
+          if (keep < 1.f) set_dropout(l.ep, keep, 32u + (uint32_t)(j - 1), l.N);
+        }
+      } else {                           // encoder layer i = 2L-1-k
+        const int i = 2 * L - 1 - k;
+        l.K = layers[i]; l.N = enc_in(i); l.ldw = l.K;
+        snprintf(wn, 32, "weights%d", i); l.Wkm = pvar(wn);                                                  // W_i stored [N, K]
+        l.ep.saved = ea[i - 1]; l.ep.lds = l.N; l.ep.act = cfg.activation;
+        if (keep < 1.f) set_dropout(l.ep, keep, (uint32_t)(i - 1), l.N);
+      }
+      if (!l.Wkm || (l.K & 3) || (l.N & 3)) return 0;
+      if (k == nops - 1) { l.ep.target = l.ep.saved; l.ep.ldt = l.ep.lds; }      // final op: the aux tile travels by TMA
+      l.ep.colsum_partials = cpch[k];
+      l.out = dch[k]; l.ldo = l.N;
+      ls.push_back(l); flops += 2.0 * l.K * l.N;
+    }
+    ChainParams cp;
+    if (!chain_build(cp, out, B, F, ls)) return 0;
+    const int grid = std::min(cp.m_tiles, num_sms);
+    cp.stagger_ns = 0u;
+    int pr = prof_begin(flops * (double)B);
+    if (pr >= 0) { auto& R = prof_recs[pr]; R.m = B; R.n = -2; R.k = -2; R.ta = 0; R.tb = 1; R.splits = 1; }
+    cudaError_t e = chain_launch(cp, grid, stream);
+    prof_end(pr);
+    ++launches; ++chain_launches; ++bchain_launches;
+    if (e != cudaSuccess) return cuda_fail(e, "backward chain launch");
+    return 1;
+  }
+
+  // Weight / bias gradients from the deltas of a backward-chain launch (same GEMMs, same order and the same buckets as
+  // the per-layer path below).
+  int backward_recon_from_chain(int64_t B) {
+    for (int j = L - 1; j >= 0; --j) {
+      const int i = L - 1 - j;
+      const int din = layers[i], dout = enc_in(i);
+      const float* d = j == L - 1 ? out : dch[L - 2 - j];
+      const float* part = j == L - 1 ? colpart : cpch[L - 2 - j];
+      char wn[32], bn[32]; snprintf(bn, 32, "decode_biases%d", i);
+      const float* u_in = j == 0 ? cur_emb : da[j - 1];
+      RET(bias_grad(d, B, dout, dout, gvar(bn), true, part));
+      Epilogue ew = epi(EPI_PLAIN);
+      if (cfg.tie_weights) {
+        snprintf(wn, 32, "weights%d", i);
+        RET(gemm(true, false, dout, din, B, d, dout, u_in, din, gvar(wn), din, noise_view(false), ew, nullptr, true));
+        RET(bucket_vars(bn, bn));
+      } else {
+        snprintf(wn, 32, "decode_weights%d", i);
+        RET(gemm(true, false, din, dout, B, u_in, din, d, dout, gvar(wn), dout, noise_view(false), ew, nullptr, true));
+        RET(bucket_vars(wn, bn));
+      }
+    }
+    for (int i = L - 1; i >= 0; --i) {
+      const int din = enc_in(i), dout = layers[i];
+      const int k = 2 * L - 2 - i;
+      char wn[32], bn[32]; snprintf(wn, 32, "weights%d", i); snprintf(bn, 32, "encode_biases%d", i);
+      const float* a_in = i == 0 ? x_eff : ea[i - 1];
+      NoiseView nv = i == 0 ? x_noise : noise_view(false);
+      RET(bias_grad(dch[k], B, dout, dout, gvar(bn), true, cpch[k]));
+      Epilogue ew = epi(EPI_PLAIN); ew.beta = cfg.tie_weights ? 1.f : 0.f;
+      RET(gemm(true, false, din, dout, B, a_in, din, dch[k], dout, gvar(wn), dout, nv, ew, nullptr, true));
+      RET(bucket_vars(wn, bn));
+    }
+    d_fused = false;
+    return 0;
+  }
+
   int backward_recon(int64_t B, float keep) {
     cls_pass = false;
+    { int cr = backward_chain(B, keep); if (cr < 0) return cr; if (cr == 1) return backward_recon_from_chain(B); }
     float* d = out; int64_t ldd = F;       // delta_L from the EPI_LOSS_TRAIN epilogue
     float* nxt = dA;
     for (int j = L - 1; j >= 0; --j) {
@@ -1682,6 +1793,7 @@ int mmae_set_shard(mmae_engine* e, int64_t global_batch, int64_t first_row) {
 
 int64_t mmae_kernel_launches(const mmae_engine* e) { return e ? e->launches : 0; }
 int64_t mmae_chain_launches(const mmae_engine* e) { return e ? e->chain_launches : 0; }
+int64_t mmae_backward_chain_launches(const mmae_engine* e) { return e ? e->bchain_launches : 0; }
 int64_t mmae_graph_replays(const mmae_engine* e) { return e ? e->graph_replays : 0; }
 int64_t mmae_fused_noise_launches(const mmae_engine* e) { return e ? e->fused_noise_launches : 0; }
 

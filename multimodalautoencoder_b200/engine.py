@@ -490,6 +490,11 @@ class Engine:
         return self.lib.mmae_graph_replays(self._h)
 
     @property
+    def backward_chain_launches(self):
+        """How many of the launches were the whole-backward (all dgrads of a step) kernel."""
+        return self.lib.mmae_backward_chain_launches(self._h)
+
+    @property
     def chain_launches(self):
         """How many of the launches were the whole-network (encode + decode + loss) kernel."""
         return self.lib.mmae_chain_launches(self._h)

@@ -152,3 +152,50 @@ def test_pipelined_host_inference_matches_single_call():
     r2 = e.forward_host(X, recon=True, embedding=True)
     assert np.array_equal(r2['recon'], wr['recon'].cpu().numpy()) and np.array_equal(r2['embedding'], wr['embedding'].cpu().numpy())
     e.close()
+
+
+BWD_CASES = [
+    dict(id='S-untied', kw=dict(tie=False, lam=0.001), B=640, keep=1.0),
+    dict(id='S-untied-dropout', kw=dict(tie=False), B=640, keep=0.5),
+    dict(id='S-tied-relu-rmse', kw=dict(tie=True, act='relu', loss='mean_squared', lam=0.001), B=1000, keep=1.0),
+    dict(id='S-tied-dropout-tanh', kw=dict(tie=True, act='tanh'), B=300, keep=0.7),
+    dict(id='S-L3-softplus', kw=dict(layers=(128, 64, 32), tie=False, act='softplus'), B=129, keep=1.0),
+    dict(id='S-L3-tied-dropout', kw=dict(layers=(128, 64, 32), tie=True), B=515, keep=0.5),
+    dict(id='odd-widths', kw=dict(layers=(100, 44), tie=False, act='softsign'), B=257, keep=1.0),
+    dict(id='S-many-tiles', kw=dict(tie=False), B=128 * 148 + 77, keep=1.0),
+]
+
+
+@pytest.mark.parametrize('case', BWD_CASES, ids=[c['id'] for c in BWD_CASES])
+def test_backward_chain_matches_oracle_and_layerwise(case):
+    """Every dgrad of the step in one launch (deltas resident in TMEM from layer to layer): gradients against the fp64
+    oracle within the tf32 tolerance (5e-3 relative Frobenius) and against the per-layer tcgen05 path (1e-3)."""
+    ocfg, ecfg = make_cfgs(precision='tf32', seed=5, **case['kw'])
+    B, keep = case['B'], case['keep']
+    rng = np.random.default_rng(21)
+    X = rng.uniform(0, 1, (B, ocfg.num_feats)).astype(np.float32)
+    P = O.init_params(ocfg, rng)
+    ec = _engine(ecfg, P, True)
+    el = _engine(ecfg, P, False)
+    for e in (ec, el):
+        e.set_rng_step(11)
+        e.gen_noise(B)
+        e.train_step(X, noise=True, keep=keep)
+    assert ec.backward_chain_launches == 1, 'the backward chain did not run'
+    assert el.backward_chain_launches == 0
+    zb, mb = ec.get_noise(B)
+    noisy = O.noise_from_descriptor(ocfg, X.astype(np.float64), zb, mb)
+    from tests.helpers import dropout_masks
+    masks = dropout_masks(ocfg, 5, 11, B, keep) if keep < 1.0 else None
+    c = O.forward(ocfg, P, noisy, X.astype(np.float64), keep, masks)
+    G = O.backward_recon(ocfg, P, c)
+    lam, tied = ocfg.weight_penalty, ocfg.tie_weights
+    sc = ec.scalars()
+    scale = sc['grad_scale'] if ocfg.loss_func == 'mean_squared' else 1.0
+    for name, _ in ec.variables():
+        gc, gl = ec.get_gradient(name).astype(np.float64), el.get_gradient(name).astype(np.float64)
+        assert np.linalg.norm(gc - gl) <= 1e-3 * max(np.linalg.norm(gl), 1e-30), name
+        l2 = (2 * lam if tied else lam) if name.startswith('weights') else (lam if 'decode_weights' in name else 0.0)
+        want = G[name] - l2 * P[name]                           # the engine folds L2 into Adam
+        assert np.linalg.norm(gc * scale - want) <= 5e-3 * max(np.linalg.norm(want), 1e-30), name
+    ec.close(); el.close()
