@@ -211,6 +211,7 @@ int mmae_set_shard(mmae_engine* e, int64_t global_batch, int64_t first_row);
 int64_t mmae_kernel_launches(const mmae_engine* e);   /* kernels launched since create */
 int64_t mmae_chain_launches(const mmae_engine* e);    /* of those, whole-network (encode+decode+loss) launches */
 int64_t mmae_backward_chain_launches(const mmae_engine* e);   /* ... and whole-backward (every dgrad of the step) launches */
+int64_t mmae_wgrad_group_launches(const mmae_engine* e);      /* ... and grouped weight-gradient (every dW of the step) launches */
 int64_t mmae_graph_replays(const mmae_engine* e);     /* train steps replayed from a captured CUDA graph (MMAE_GRAPHS=0 disables) */
 int64_t mmae_fused_noise_launches(const mmae_engine* e); /* GEMM launches that applied mask + noise in their A-operand load (:668-702) */
 /* Device-side timing of the tcgen05 GEMM launches (CUDA events on the engine's stream around each

@@ -83,6 +83,7 @@ PROTOTYPES = {
     'mmae_kernel_launches': (_L, [_P]),
     'mmae_chain_launches': (_L, [_P]),
     'mmae_backward_chain_launches': (_L, [_P]),
+    'mmae_wgrad_group_launches': (_L, [_P]),
     'mmae_graph_replays': (_L, [_P]),
     'mmae_fused_noise_launches': (_L, [_P]),
     'mmae_set_profiling': (_I, [_P, _I]),

@@ -20,6 +20,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "chain_tc.cuh"
+#include "wgrad_group.cuh"
 #include "kernels.cuh"
 
 using namespace mmae;
@@ -129,7 +130,7 @@ struct mmae_engine {
   // ---- CUDA graphs of the train steps (small batches are launch-bound: ~60 launches per step)
   struct GraphKey { int kind; const void* X; const void* Y; const void* T; int64_t B; int noise; float keep; int64_t gb, fr; void* stream;
     bool operator==(const GraphKey& o) const { return kind == o.kind && X == o.X && Y == o.Y && T == o.T && B == o.B && noise == o.noise && keep == o.keep && gb == o.gb && fr == o.fr && stream == o.stream; } };
-  struct GraphEntry { GraphKey key; int seen = 0; cudaGraphExec_t exec = nullptr; int64_t n_launches = 0, n_chain = 0, n_bchain = 0; int opt = 0;
+  struct GraphEntry { GraphKey key; int seen = 0; cudaGraphExec_t exec = nullptr; int64_t n_launches = 0, n_chain = 0, n_bchain = 0, n_wgroup = 0; int opt = 0;
     std::vector<char> dirty_after; bool d_fused_after = false, last_tc_after = false; };
   std::vector<GraphEntry> graphs;
   cudaStream_t gstream = nullptr;   // graphs cannot be captured on the legacy default stream: a blocking stream of our own
@@ -315,7 +316,7 @@ struct mmae_engine {
     CK(cudaMalloc(&d_state, sizeof(StepState))); CK(cudaMemset(d_state, 0, sizeof(StepState)));
     for (int o = 0; o < 2; ++o) {
       std::vector<AdamSeg> segs;
-      for (auto& v : vars) { AdamSeg s; s.begin = v.off; s.l2 = v.l2[o]; s.pad = 0.f; segs.push_back(s); }
+      for (auto& v : vars) { AdamSeg s; s.begin = v.off; s.l2 = v.l2[o]; s.pad = 0.f; s.rows = (int)v.rows; s.cols = (int)v.cols; segs.push_back(s); }
       nsegs[o] = (int)segs.size();
       CK(cudaMalloc(&d_segs[o], segs.size() * sizeof(AdamSeg)));
       CK(cudaMemcpy(d_segs[o], segs.data(), segs.size() * sizeof(AdamSeg), cudaMemcpyHostToDevice));
@@ -452,7 +453,7 @@ struct mmae_engine {
     fr(d_state); fr(PT); fr(colpart); fr(P); fr(G); fr(M0); fr(V0); fr(M1); fr(V1); fr(d_scalars); fr(d_sums); fr(d_segs[0]); fr(d_segs[1]);
     fr(d_col_mod); fr(d_starts); fr(zero_bits); fr(mod_bits); fr(miss_bits);
     for (int i = 0; i < 2; ++i) { fr(xin[i]); fr(yin[i]); fr(ds_X[i]); fr(ds_Y[i]); }
-    fr(noisy); fr(gxb); fr(gyb);
+    fr(noisy); fr(gxb); fr(gyb); fr(wg_ws);
     for (auto q : dch) fr(q); for (auto q : cpch) fr(q);
     for (auto p : ea) fr(p); for (auto p : da) fr(p); for (auto p : ha) fr(p);
     fr(mu); fr(lv); fr(eps); fr(emb); fr(glv); fr(out); fr(dA); fr(dB);
@@ -517,6 +518,20 @@ struct mmae_engine {
   bool starts_aligned32() const { for (int v : starts) if (v & 31) return false; return true; }
   bool last_gemm_tc = false;
   bool d_fused = false;      // the current delta's column-sum partials are valid in colpart
+  // Small models: Adam rewrites the K-major weight shadows in the same pass (scattered 4-byte stores beat a launch);
+  // the shadows are then always current outside a step, and captured graphs need no transpose launch.
+  bool shadow_in_adam() const { return cfg.precision == MMAE_PREC_TF32 && nP <= ((int64_t)1 << 21); }
+  // Fast small-config train step (train_core only, no data parallelism): the loss partials of the forward chain are
+  // summed, and the per-step scalars finalised, inside grad_assemble_kernel instead of in launches of their own.
+  bool fast_step = false;
+  int64_t pending_loss_partials = 0;     // > 0: partials[0..n) still have to be summed into d_sums[0]
+  bool step_finalized = false;           // grad_assemble_kernel already did finalize_scalars' work for this step
+  int flush_pending_loss() {
+    if (pending_loss_partials > 0) { int64_t n = pending_loss_partials; pending_loss_partials = 0; return reduce_partials(n, 0); }
+    return 0;
+  }
+  float* wg_ws = nullptr; int64_t wg_ws_cap = 0;
+  int64_t wgroup_launches = 0;
 
   // ================================================================= GEMM dispatch
   // C = opA(A) opB(B) with epilogue.  n_partials receives the number of loss partials written.
@@ -609,6 +624,7 @@ struct mmae_engine {
     bool decoder; bool headp; float* recon_out;
     float* fill_out = nullptr;     // whole-network kernel: write the filled matrix (A15) instead of decoded_X
     bool need_mu = true;           // the embedding is wanted in global memory (it is not for plain predict / fill-in)
+    bool noisy_ready = false;      // `noisy` already holds the noisy batch of X (sample_noise_kernel drew and applied it)
   };
 
   int begin_step(int64_t B, bool noise) {
@@ -665,7 +681,7 @@ struct mmae_engine {
     if (!stream && !gstream) CK(cudaStreamCreate(&gstream));
     cudaStream_t cs = stream ? stream : gstream;
     if (ge->exec) {                                              // replay + the host-side effects of one step
-      rng_step += 1; t_opt[ge->opt] += 1; launches += ge->n_launches; chain_launches += ge->n_chain; bchain_launches += ge->n_bchain; last_B = B;
+      rng_step += 1; t_opt[ge->opt] += 1; launches += ge->n_launches; chain_launches += ge->n_chain; bchain_launches += ge->n_bchain; wgroup_launches += ge->n_wgroup; last_B = B;
       pt_dirty = ge->dirty_after; d_fused = ge->d_fused_after; last_gemm_tc = ge->last_tc_after;
       ++graph_replays;
       CK(cudaGraphLaunch(ge->exec, cs));
@@ -673,8 +689,9 @@ struct mmae_engine {
     }
     // capture.  All K-major weight shadows are forced stale so that the graph always refreshes the ones it reads.
     const size_t idx = (size_t)(ge - graphs.data());
-    std::fill(pt_dirty.begin(), pt_dirty.end(), 1);
-    const int64_t l0 = launches, c0 = chain_launches, bc0 = bchain_launches, cap0 = cap, capa0 = cap_acts, caph0 = cap_host, sk0 = splitk_cap;
+    if (!shadow_in_adam()) std::fill(pt_dirty.begin(), pt_dirty.end(), 1);
+    else { int rr = refresh_shadows(); if (rr) return rr; }     // (current outside steps: set_variable refreshes eagerly, Adam rewrites them)
+    const int64_t l0 = launches, c0 = chain_launches, bc0 = bchain_launches, wg0 = wgroup_launches, cap0 = cap, capa0 = cap_acts, caph0 = cap_host, sk0 = splitk_cap;
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
     if (ce != cudaSuccess) { (void)cudaGetLastError(); graph_mode = 0; return body(); }
@@ -694,7 +711,7 @@ struct mmae_engine {
     ce = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { g.exec = nullptr; graph_mode = 0; return cuda_fail(ce, "cudaGraphInstantiate"); }
-    g.n_launches = launches - l0; g.n_chain = chain_launches - c0; g.n_bchain = bchain_launches - bc0;
+    g.n_launches = launches - l0; g.n_chain = chain_launches - c0; g.n_bchain = bchain_launches - bc0; g.n_wgroup = wgroup_launches - wg0;
     g.dirty_after = pt_dirty; g.d_fused_after = d_fused; g.last_tc_after = last_gemm_tc;
     CK(cudaGraphLaunch(g.exec, cs));
     return 0;
@@ -703,6 +720,27 @@ struct mmae_engine {
   // Whole-network launch (chain_tc.cuh): encoder + decoder + loss in one persistent tcgen05 kernel, activations
   // resident in TMEM.  Returns 1 when it ran, 0 when the configuration does not fit (caller runs the per-layer
   // GEMMs), or a (negative) error code.
+  // debug timeline of CTA 0 (MMAE_CHAIN_TRACE=1): clock64 deltas per tile and op
+  long long* trace_begin(ChainParams& cp) {
+    static const bool want_trace = getenv("MMAE_CHAIN_TRACE") != nullptr;
+    if (!want_trace) return nullptr;
+    long long* trace = nullptr;
+    cudaMalloc(&trace, 64 * CH_MAX_OPS * 4 * 8); cudaMemsetAsync(trace, 0, 64 * CH_MAX_OPS * 4 * 8, stream); cp.trace = trace;
+    return trace;
+  }
+  void trace_end(const ChainParams& cp, long long* trace, const char* tag) {
+    if (!trace) return;
+    std::vector<long long> h(64 * CH_MAX_OPS * 4);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost); cudaFree(trace);
+    const long long t0 = h[0];
+    for (int it = 0; it < 8 && it * num_sms < cp.m_tiles; ++it)
+      for (int i = 0; i < cp.nops; ++i) {
+        const long long* q = &h[(it * CH_MAX_OPS + i) * 4];
+        fprintf(stderr, "[chain trace %s] tile %d op %d: mma start %8lld issued %8lld | epi start %8lld end %8lld\n", tag, it, i,
+                q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0);
+      }
+  }
   int64_t chain_launches = 0;
   int64_t fused_noise_launches = 0;      // two-SM GEMM launches that applied the mask + noise to their A tile in shared memory
   int chain_mode = -1;
@@ -762,34 +800,24 @@ struct mmae_engine {
     if (!chain_build(cp, a, B, F, ls)) return 0;
     if (o.fill_out && M <= 32) { cp.scan_miss = 1; cp.num_mod = M; cp.starts = d_starts; }
     const int grid = std::min(cp.m_tiles, num_sms);
-    static const bool want_trace = getenv("MMAE_CHAIN_TRACE") != nullptr;
     static const int chain_stagger = getenv("MMAE_CHAIN_STAGGER") ? atoi(getenv("MMAE_CHAIN_STAGGER")) : 60;
     cp.stagger_ns = cp.m_tiles >= 8 * grid ? (unsigned)chain_stagger : 0u;
-    long long* trace = nullptr;
-    if (want_trace) { cudaMalloc(&trace, 64 * CH_MAX_OPS * 4 * 8); cudaMemsetAsync(trace, 0, 64 * CH_MAX_OPS * 4 * 8, stream); cp.trace = trace; }
+    long long* trace = trace_begin(cp);
     int pr = prof_begin(flops * (double)B);
     if (pr >= 0) { auto& R = prof_recs[pr]; R.m = B; R.n = -1; R.k = -1; R.ta = 0; R.tb = 1; R.splits = 1; }
     cudaError_t e = chain_launch(cp, grid, stream);
     prof_end(pr);
     ++launches; ++chain_launches;
     if (e != cudaSuccess) return cuda_fail(e, "chain launch");
-    if (trace) {      // debug timeline of CTA 0 (MMAE_CHAIN_TRACE=1): clock64 deltas per tile and op
-      std::vector<long long> h(64 * CH_MAX_OPS * 4);
-      cudaStreamSynchronize(stream);
-      cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost); cudaFree(trace);
-      const long long t0 = h[0];
-      for (int it = 0; it < 8 && it * num_sms < cp.m_tiles; ++it)
-        for (int i = 0; i < cp.nops; ++i) {
-          const long long* q = &h[(it * CH_MAX_OPS + i) * 4];
-          fprintf(stderr, "[chain trace] tile %d op %d: mma start %8lld issued %8lld | epi start %8lld end %8lld\n", it, i,
-                  q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0);
-        }
-    }
+    trace_end(cp, trace, "fwd");
     cur_emb = mu;
     d_fused = o.train_recon;
     last_gemm_tc = true;
     fill_fused = o.fill_out != nullptr;
-    if (o.target) { int r = reduce_partials(grid, 0); if (r) return r; }
+    if (o.target) {
+      if (fast_step && o.train_recon) pending_loss_partials = grid;        // summed by grad_assemble_kernel
+      else { int r = reduce_partials(grid, 0); if (r) return r; }
+    }
     return 1;
   }
 
@@ -807,8 +835,10 @@ struct mmae_engine {
                             (F & 31) == 0 && layers[0] > 256 && (layers[0] & 3) == 0;
     if (o.noise && cfg.precision == MMAE_PREC_TF32 && B >= 32 && (F & 3) == 0 && !fuse_noise) {
       // the tcgen05 family reads its operands through TMA: materialise noisy_X once (first GEMM + its wgrad)
-      noise_apply_kernel<<<grid_for(B * F, 256), 256, 0, stream>>>(o.X, noisy, B, F, nv);
-      CKL("noise_apply");
+      if (!o.noisy_ready) {
+        noise_apply_kernel<<<grid_for(B * F, 256), 256, 0, stream>>>(o.X, noisy, B, F, nv);
+        CKL("noise_apply");
+      }
       a = noisy; nv.enabled = 0;
     }
     x_eff = a; x_noise = nv;
@@ -990,18 +1020,121 @@ struct mmae_engine {
     if (!chain_build(cp, out, B, F, ls)) return 0;
     const int grid = std::min(cp.m_tiles, num_sms);
     cp.stagger_ns = 0u;
+    long long* trace = trace_begin(cp);
     int pr = prof_begin(flops * (double)B);
     if (pr >= 0) { auto& R = prof_recs[pr]; R.m = B; R.n = -2; R.k = -2; R.ta = 0; R.tb = 1; R.splits = 1; }
     cudaError_t e = chain_launch(cp, grid, stream);
     prof_end(pr);
     ++launches; ++chain_launches; ++bchain_launches;
     if (e != cudaSuccess) return cuda_fail(e, "backward chain launch");
+    trace_end(cp, trace, "bwd");
     return 1;
   }
 
   // Weight / bias gradients from the deltas of a backward-chain launch (same GEMMs, same order and the same buckets as
   // the per-layer path below).
+  // All weight gradients of the step in ONE grouped tcgen05 launch (wgrad_group.cuh) + ONE assembly launch that sums
+  // the split-K slices and the bias-gradient partials into G (and, on the fast train path, the loss partials and the
+  // per-step scalars).  Returns 1 when it ran, 0 when a shape does not fit (the per-layer GEMMs run instead).
+  int backward_group(int64_t B) {
+    static const bool group_off = getenv("MMAE_WGRAD_GROUP") && getenv("MMAE_WGRAD_GROUP")[0] == '0';
+    if (group_off || dp_on() || x_noise.enabled) return 0;
+    const bool tied = cfg.tie_weights != 0;
+    struct Item { WgDesc d; Var* v; };
+    std::vector<Item> items;
+    char wn[32];
+    auto dec_item = [&](int i) {            // decoder layer j = L-1-i
+      const int j = L - 1 - i;
+      const int din = layers[i], dout = enc_in(i);
+      const float* d = j == L - 1 ? out : dch[L - 2 - j];
+      const float* u_in = j == 0 ? cur_emb : da[j - 1];
+      Item it; memset(&it.d, 0, sizeof(it.d));
+      if (tied) { snprintf(wn, 32, "weights%d", i); it.d.A = d; it.d.lda = dout; it.d.M = dout; it.d.B = u_in; it.d.ldb = din; it.d.N = din; }
+      else { snprintf(wn, 32, "decode_weights%d", i); it.d.A = u_in; it.d.lda = din; it.d.M = din; it.d.B = d; it.d.ldb = dout; it.d.N = dout; }
+      it.v = find(wn); items.push_back(it);
+    };
+    auto enc_item = [&](int i) {
+      const int din = enc_in(i), dout = layers[i];
+      const int k = 2 * L - 2 - i;
+      Item it; memset(&it.d, 0, sizeof(it.d));
+      snprintf(wn, 32, "weights%d", i);
+      it.d.A = i == 0 ? x_eff : ea[i - 1]; it.d.lda = din; it.d.M = din; it.d.B = dch[k]; it.d.ldb = dout; it.d.N = dout;
+      it.v = find(wn); items.push_back(it);
+    };
+    if (tied) { for (int i = 0; i < L; ++i) { dec_item(i); enc_item(i); } }
+    else { for (int i = 0; i < L; ++i) dec_item(i); for (int i = 0; i < L; ++i) enc_item(i); }
+    if ((int)items.size() > WG_MAX_PROBLEMS || (int)items.size() + 2 * L > GA_MAX_SEGS) return 0;
+    std::vector<WgDesc> descs;
+    for (auto& it : items) { if (!it.v || !wg_eligible(it.d)) return 0; descs.push_back(it.d); }
+    const WgPlan pl = wg_plan(descs, B, num_sms);
+    int64_t need = 0;
+    for (auto& it : items) need += (int64_t)pl.splits * it.d.M * it.d.N;
+    if (need > wg_ws_cap) {
+      CK(cudaStreamSynchronize(stream)); clear_graphs();
+      RET(realloc_dev(wg_ws, need)); wg_ws_cap = need;
+    }
+    WgParams wp; memset(&wp, 0, sizeof(wp));
+    wp.nprob = (int)items.size(); wp.splits = pl.splits; wp.K = B; wp.k_per_split = pl.k_per_split;
+    GaArgs ga; memset(&ga, 0, sizeof(ga));
+    ga.G = G;
+    int tile0 = 0, nblk = 1; int64_t off = 0;
+    for (size_t q = 0; q < items.size(); ++q) {
+      const WgDesc& d = items[q].d;
+      WgProblem& P = wp.pr[q];
+      P.M = d.M; P.N = d.N; P.m_blocks = (d.M + TC_BM - 1) / TC_BM; P.n_blocks = (d.N + WG_BN - 1) / WG_BN;
+      P.tile0 = tile0; tile0 += P.m_blocks * P.n_blocks;
+      P.a3d = (d.M % 32) == 0; P.b3d = (d.N % 32) == 0;
+      P.ws = wg_ws + off;
+      bool ok = P.a3d ? make_tmap_mn3d(&P.tmA, d.A, B, d.M, d.lda, TC_BK, TC_BM / 32) : make_tmap(&P.tmA, d.A, B, d.M, d.lda, 32, TC_BK, true);
+      ok = ok && (P.b3d ? make_tmap_mn3d(&P.tmB, d.B, B, d.N, d.ldb, TC_BK, WG_BN / 32) : make_tmap(&P.tmB, d.B, B, d.N, d.ldb, 32, TC_BK, true));
+      if (!ok) return 0;
+      const bool first_of_var = q == 0 || items[q - 1].v != items[q].v;
+      if (first_of_var) {
+        GaSeg& sg = ga.seg[ga.nseg++];
+        sg.g_off = items[q].v->off; sg.count = (int64_t)d.M * d.N; sg.src = P.ws; sg.nslices = pl.splits; sg.kind = 0;
+        sg.block0 = nblk; sg.nblocks = (int)std::min<int64_t>(64, (sg.count + 255) / 256); nblk += sg.nblocks;
+      } else {
+        ga.seg[ga.nseg - 1].nslices += pl.splits;          // tied: decoder part + encoder part, adjacent slice lists
+      }
+      off += (int64_t)pl.splits * d.M * d.N;
+    }
+    wp.tiles = tile0;
+    const int groups = (int)((B + 31) / 32);
+    auto bias_seg = [&](const char* name, const float* part, int n) {
+      Var* v = find(name);
+      GaSeg& sg = ga.seg[ga.nseg++];
+      sg.g_off = v->off; sg.count = n; sg.src = part; sg.nslices = groups; sg.kind = 1;
+      sg.block0 = nblk; sg.nblocks = (n + 31) / 32; nblk += sg.nblocks;
+    };
+    char bn[32];
+    for (int i = 0; i < L; ++i) {
+      const int j = L - 1 - i;
+      snprintf(bn, 32, "decode_biases%d", i); bias_seg(bn, j == L - 1 ? colpart : cpch[L - 2 - j], enc_in(i));
+      snprintf(bn, 32, "encode_biases%d", i); bias_seg(bn, cpch[2 * L - 2 - i], layers[i]);
+    }
+    double flops = 0.0;
+    for (auto& it : items) flops += 2.0 * it.d.M * it.d.N * (double)B;
+    int pr = prof_begin(flops);
+    if (pr >= 0) { auto& R = prof_recs[pr]; R.m = -3; R.n = wp.tiles; R.k = B; R.ta = 1; R.tb = 0; R.splits = pl.splits; }
+    cudaError_t e = wgrad_group_launch(wp, pl.grid, stream);
+    prof_end(pr);
+    ++launches; ++wgroup_launches;
+    if (e != cudaSuccess) return cuda_fail(e, "grouped wgrad launch");
+    if (pending_loss_partials > 0) {
+      ga.loss_partials = partials; ga.n_loss_partials = (int)pending_loss_partials; ga.loss_sum_out = d_sums + 0;
+      pending_loss_partials = 0;
+    }
+    ga.do_finalize = fast_step ? 1 : 0;
+    FinalizeArgs fin = finalize_args(B, true, false, fast_step ? 0 : -1, fast_step);
+    grad_assemble_kernel<<<nblk, 256, 0, stream>>>(ga, fin);
+    CKL("grad_assemble");
+    if (fast_step) step_finalized = true;
+    d_fused = false;
+    return 1;
+  }
+
   int backward_recon_from_chain(int64_t B) {
+    { int gr = backward_group(B); if (gr < 0) return gr; if (gr == 1) return 0; }
     for (int j = L - 1; j >= 0; --j) {
       const int i = L - 1 - j;
       const int din = layers[i], dout = enc_in(i);
@@ -1157,13 +1290,17 @@ struct mmae_engine {
   int allreduce_grads() { return join_comm(); }
   // fuse_opt >= 0: the kernel also advances that optimizer's step count / alpha (adam_prep) and, with fuse_advance, the
   // Philox step -- two launches fewer per train step.
-  int finalize_scalars(int64_t B, bool recon, bool headl, int fuse_opt = -1, bool fuse_advance = false) {
+  FinalizeArgs finalize_args(int64_t B, bool recon, bool headl, int fuse_opt, bool fuse_advance) const {
     FinalizeArgs a; a.sums = d_sums; a.scalars = d_scalars; a.loss = cfg.loss_func; a.variational = cfg.variational;
     a.state = (fuse_opt >= 0 || fuse_advance) ? d_state : nullptr; a.prep_opt = fuse_opt; a.advance = fuse_advance ? 1 : 0;
     a.lr = fuse_opt == 1 ? cfg.head_learning_rate : cfg.learning_rate; a.b1 = cfg.beta1; a.b2 = cfg.beta2;
     a.n_elems = (double)gbatch(B) * F; a.batch = (double)gbatch(B);
     a.head_count = cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? (double)gbatch(B) * std::max(C, 1) : (double)gbatch(B);
     a.do_recon = recon ? 1 : 0; a.do_head = headl ? 1 : 0;
+    return a;
+  }
+  int finalize_scalars(int64_t B, bool recon, bool headl, int fuse_opt = -1, bool fuse_advance = false) {
+    FinalizeArgs a = finalize_args(B, recon, headl, fuse_opt, fuse_advance);
     finalize_scalars_kernel<<<1, 1, 0, stream>>>(a); CKL("finalize_scalars"); return 0;
   }
 
@@ -1183,9 +1320,11 @@ struct mmae_engine {
     a.n_elems = (double)gbatch(B) * F;
     a.alpha = &d_state->alpha[opt];
     a.b1 = cfg.beta1; a.b2 = cfg.beta2; a.eps = cfg.adam_eps; a.scalars_out = d_scalars;
+    a.PT = shadow_in_adam() ? PT : nullptr;
     adam_kernel<<<grid_for(a.end - a.begin, 256), 256, 0, stream>>>(a);
     CKL("adam");
-    mark_dirty(a.begin, a.end);
+    if (a.PT) { for (size_t i = 0; i < vars.size(); ++i) if (vars[i].off >= a.begin && vars[i].off < a.end) pt_dirty[i] = 0; }
+    else mark_dirty(a.begin, a.end);
     return 0;
   }
   int64_t last_B = 0;
@@ -1330,7 +1469,11 @@ static int var_copy(mmae_engine* e, const char* name, float* base, int64_t base_
 int mmae_set_variable(mmae_engine* e, const char* name, const float* host, int64_t count) {
   ENTER(e);
   int r = var_copy(e, name, e->P, 0, const_cast<float*>(host), count, true);
-  if (r == 0) e->mark_dirty(0, e->nP);
+  if (r == 0) {
+    Var* v = e->find(name);
+    e->mark_dirty(v->off, v->off + 1);
+    if (e->shadow_in_adam() && v->cols > 0) r = e->refresh_shadows();      // keep "shadows are current outside a step" true
+  }
   return r;
 }
 int mmae_get_variable(mmae_engine* e, const char* name, float* host, int64_t count) {
@@ -1519,9 +1662,13 @@ int mmae_apply_update(mmae_engine* e, int optimizer) {
 
 namespace {
 int train_core(mmae_engine* e, const float* Xd, const float* target, int64_t batch, int use_noise, float keep) {
-  int r = do_train(e, Xd, batch, use_noise, keep, target, true); if (r) return r;
+  e->fast_step = !e->dp_on(); e->step_finalized = false; e->pending_loss_partials = 0;
+  int r = do_train(e, Xd, batch, use_noise, keep, target, true);
+  e->fast_step = false;
+  if (r) return r;
+  r = e->flush_pending_loss(); if (r) return r;
   r = e->allreduce_grads(); if (r) return r;
-  r = e->finalize_scalars(batch, true, false, 0, true); if (r) return r;
+  if (!e->step_finalized) { r = e->finalize_scalars(batch, true, false, 0, true); if (r) return r; }
   return e->apply_update(0, batch, true);
 }
 int cls_core(mmae_engine* e, const float* Xd, const float* Yd, int64_t batch, int use_noise, float keep) {
@@ -1794,6 +1941,7 @@ int mmae_set_shard(mmae_engine* e, int64_t global_batch, int64_t first_row) {
 int64_t mmae_kernel_launches(const mmae_engine* e) { return e ? e->launches : 0; }
 int64_t mmae_chain_launches(const mmae_engine* e) { return e ? e->chain_launches : 0; }
 int64_t mmae_backward_chain_launches(const mmae_engine* e) { return e ? e->bchain_launches : 0; }
+int64_t mmae_wgrad_group_launches(const mmae_engine* e) { return e ? e->wgroup_launches : 0; }
 int64_t mmae_graph_replays(const mmae_engine* e) { return e ? e->graph_replays : 0; }
 int64_t mmae_fused_noise_launches(const mmae_engine* e) { return e ? e->fused_noise_launches : 0; }
 

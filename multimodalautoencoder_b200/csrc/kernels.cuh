@@ -87,6 +87,95 @@ __global__ void noise_apply_kernel(const float* __restrict__ X, float* __restric
   }
 }
 
+// One pass that produces everything a train step needs from its batch: optional row sampling (Philox indices into a
+// resident dataset, data_funcs.py:167) + the row's noise descriptor (:668-702) + the clean batch (loss target) + the
+// noisy batch (first GEMM operand and its weight gradient).  One warp per row; the row's zero bitmap is built in shared
+// memory, so the descriptor is drawn and applied without a round trip through global memory.  Bit-identical to
+// philox_indices_kernel + gather_rows_kernel + noise_gen_kernel + noise_apply_kernel run one after the other.
+struct SampleNoiseArgs {
+  NoiseGenArgs g;                 // descriptor parameters; g.zero_bits / g.mod_bits still receive the descriptor
+  const float* src;               // dataset [n_rows, F] (gather) or the batch itself [batch, F]
+  uint32_t n_rows;                // > 0: sample row indices into src;  0: src is the batch
+  const int64_t* idx_in;          // optional host-supplied indices (n_rows > 0)
+  int64_t* idx_out;               // optional: the sampled indices
+  float* clean_out;               // gathered clean batch (null when src is the batch)
+  float* noisy_out;               // noisy batch
+  const uint8_t* col_mod; float mask_with;
+};
+constexpr int SN_WARPS = 8;
+constexpr int SN_MAX_ZW = 128;      // F <= 4096
+__global__ void __launch_bounds__(SN_WARPS * 32) sample_noise_kernel(const SampleNoiseArgs a) {
+  __shared__ uint32_t zsm[SN_WARPS][SN_MAX_ZW];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * SN_WARPS;
+  const uint32_t step = __ldg(a.g.step);
+  const int F = a.g.num_feats, zw = a.g.zw;
+  for (int64_t row = (int64_t)blockIdx.x * SN_WARPS + wl; row < a.g.batch; row += nwarps) {
+    const int64_t grow = row + a.g.row0;
+    uint32_t* zb = zsm[wl];
+    for (int w = lane; w < zw; w += 32) zb[w] = 0u;
+    __syncwarp();
+    const int q = (a.g.n_zero + 3) >> 2;
+    for (int c = lane; c < q; c += 32) {
+      Philox4 p = philox4x32((uint64_t)grow * q + c, kStreamZero, step, a.g.seed);
+      uint32_t wv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        int j = c * 4 + l;
+        if (j < a.g.n_zero) {
+          uint32_t col = mulhi_u32(wv[l], (uint32_t)F);
+          atomicOr(zb + (col >> 5), 1u << (col & 31));
+        }
+      }
+    }
+    uint32_t mb = 0u;
+    {
+      Philox4 p = philox4x32((uint64_t)grow, kStreamMod, step, a.g.seed);      // every lane draws the same word: no shuffle needed
+      if (a.g.mode == MMAE_NOISE_INTELLIGENT) {
+        int k = 0;
+        for (int t = 0; t < a.g.num_types - 1; ++t) k += (p.x >= a.g.thresholds[t]) ? 1 : 0;
+        mb = a.g.type_masks[k];
+      } else {
+        uint32_t wv[4] = {p.x, p.y, p.z, p.w};
+        for (int d = 0; d < a.g.num_drop; ++d) mb |= 1u << mulhi_u32(wv[d], (uint32_t)a.g.num_mod);
+      }
+    }
+    int64_t srow = row;
+    if (a.n_rows) {
+      srow = a.idx_in ? a.idx_in[row] : (int64_t)mulhi_u32(philox_word((uint64_t)grow, kStreamBatch, step, a.g.seed), a.n_rows);
+      if (lane == 0 && a.idx_out) a.idx_out[row] = srow;
+    }
+    __syncwarp();
+    if (lane == 0) a.g.mod_bits[row] = mb;
+    for (int w = lane; w < zw; w += 32) a.g.zero_bits[row * zw + w] = zb[w];
+    const float* x = a.src + srow * (int64_t)F;
+    float* o = a.noisy_out + row * (int64_t)F;
+    float* cl = a.clean_out ? a.clean_out + row * (int64_t)F : nullptr;
+    if ((F & 3) == 0) {
+      for (int c4 = lane; c4 < (F >> 2); c4 += 32) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(x) + c4);
+        if (cl) reinterpret_cast<float4*>(cl)[c4] = v;
+        const int c = c4 << 2;
+        const uint32_t z = zb[c >> 5] >> (c & 31);
+        const uchar4 m = *reinterpret_cast<const uchar4*>(a.col_mod + c);
+        v.x = ((mb >> m.x) & 1u) ? a.mask_with : ((z & 1u) ? 0.f : v.x);
+        v.y = ((mb >> m.y) & 1u) ? a.mask_with : ((z & 2u) ? 0.f : v.y);
+        v.z = ((mb >> m.z) & 1u) ? a.mask_with : ((z & 4u) ? 0.f : v.z);
+        v.w = ((mb >> m.w) & 1u) ? a.mask_with : ((z & 8u) ? 0.f : v.w);
+        reinterpret_cast<float4*>(o)[c4] = v;
+      }
+    } else {
+      for (int c = lane; c < F; c += 32) {
+        float v = __ldg(x + c);
+        if (cl) cl[c] = v;
+        const bool zz = (zb[c >> 5] >> (c & 31)) & 1u;
+        o[c] = ((mb >> a.col_mod[c]) & 1u) ? a.mask_with : (zz ? 0.f : v);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // out[c][r] = in[r][c]  (K-major shadows of the weights for the tcgen05 forward GEMMs)
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
   __shared__ float t[32][33];
@@ -312,7 +401,7 @@ __global__ void head_loss_kernel(const HeadLossArgs a) {
 // ------------------------------------------------------------------ fused scale + L2 + TF-Adam (:411, :443)
 // tf.train.AdamOptimizer._apply_dense:  a_t = lr*sqrt(1-b2^t)/(1-b1^t);  m += (g-m)(1-b1);
 // v += (g^2-v)(1-b2);  theta -= a_t * m / (sqrt(v)+eps).   g = scale*G + l2[seg]*theta.
-struct AdamSeg { int64_t begin; float l2; float pad; };
+struct AdamSeg { int64_t begin; float l2; float pad; int rows, cols; };      // rows / cols of a 2-D variable (cols = 0: vector)
 struct AdamArgs {
   float* P; const float* G; float* M; float* V;
   int64_t begin, end;            // flat range inside P / G;  M, V are indexed from 0 at `begin`
@@ -323,6 +412,7 @@ struct AdamArgs {
   const float* alpha;            // lr * sqrt(1 - b2^t) / (1 - b1^t), written by adam_prep_kernel for this step
   float b1, b2, eps;
   double* scalars_out;           // MMAE_S_* slots, written by thread 0
+  float* PT;                     // when set: the K-major shadow of every 2-D variable is refreshed in the same pass
 };
 __global__ void adam_kernel(const AdamArgs a) {
   float scale = 1.f;
@@ -340,7 +430,16 @@ __global__ void adam_kernel(const AdamArgs a) {
     m += (g - m) * (1.f - a.b1);
     v += (g * g - v) * (1.f - a.b2);
     a.M[i] = m; a.V[i] = v;
-    a.P[gi] = p - alpha * m / (sqrtf(v) + a.eps);
+    const float pn = p - alpha * m / (sqrtf(v) + a.eps);
+    a.P[gi] = pn;
+    if (a.PT && a.segs[lo].cols > 0) {            // small models: scattered 4-byte stores are cheaper than a launch
+      const int64_t loc = gi - a.segs[lo].begin;
+      const int cols = a.segs[lo].cols, rows = a.segs[lo].rows;
+      if (loc < (int64_t)rows * cols) {
+        const int r = (int)(loc / cols), c = (int)(loc - (int64_t)r * cols);
+        a.PT[a.segs[lo].begin + (int64_t)c * rows + r] = pn;
+      }
+    }
   }
 }
 
@@ -353,6 +452,25 @@ __global__ void adam_prep_kernel(StepState* s, int opt, double lr, double b1, do
   s->alpha[opt] = (float)(lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t)));
 }
 
+// ------------------------------------------------------------------ gradient assembly (small-config train step)
+// One launch between the grouped weight-gradient GEMM and Adam:  block 0 sums the loss partials in a fixed order and
+// does the per-step scalar bookkeeping (finalize_scalars_kernel's job);  weight segments sum their split-K slices in
+// slice order;  bias segments sum the per-32-row column-sum partials the chain kernels left behind (8 row lanes per
+// column, combined in a fixed tree).  Everything is fixed-order, hence deterministic.
+struct GaSeg {
+  int64_t g_off, count;      // destination range in G
+  const float* src;          // weights: slices [nslices][count];  biases: partials [nslices][count]
+  int nslices;
+  int kind;                  // 0 weight, 1 bias
+  int block0, nblocks;
+};
+constexpr int GA_MAX_SEGS = 24;
+struct GaArgs {
+  GaSeg seg[GA_MAX_SEGS]; int nseg;
+  float* G;
+  const float* loss_partials; int n_loss_partials; double* loss_sum_out;     // optional (null / 0: sums already there)
+  int do_finalize;
+};
 // ------------------------------------------------------------------ fill-in (data_funcs.py:310-381)
 // miss[r] bit m set iff sum(x[r, s_m:e_m]) == -(e_m - s_m); one warp per row, lanes stride the block.
 __global__ void missing_bits_kernel(const float* __restrict__ X, int64_t batch, int num_feats,
@@ -418,7 +536,10 @@ struct FinalizeArgs {
   // end-of-step bookkeeping folded into this single-thread kernel (small-batch steps are launch-latency bound):
   StepState* state; int prep_opt; double lr, b1, b2; int advance;      // prep_opt >= 0: ++t, alpha for that optimizer; advance: ++step
 };
-__global__ void finalize_scalars_kernel(FinalizeArgs a) {
+__device__ __forceinline__ void finalize_scalars_body(const FinalizeArgs& a);
+__global__ void finalize_scalars_kernel(FinalizeArgs a) { finalize_scalars_body(a); }
+
+__device__ __forceinline__ void finalize_scalars_body(const FinalizeArgs& a) {
   if (a.do_recon) {
     if (a.loss == MMAE_LOSS_RMSE) { a.scalars[MMAE_S_SUMSQ] = a.sums[0]; a.scalars[MMAE_S_RECON_LOSS] = sqrt(a.sums[0] / a.n_elems); }
     else { a.scalars[MMAE_S_SUMSQ] = 0.0; a.scalars[MMAE_S_RECON_LOSS] = a.sums[0]; }
@@ -434,6 +555,51 @@ __global__ void finalize_scalars_kernel(FinalizeArgs a) {
       a.state->alpha[a.prep_opt] = (float)(a.lr * sqrt(1.0 - pow(a.b2, (double)t)) / (1.0 - pow(a.b1, (double)t)));
     }
     if (a.advance) a.state->step += 1u;
+  }
+}
+
+__global__ void __launch_bounds__(256) grad_assemble_kernel(const GaArgs a, const FinalizeArgs fin) {
+  if (blockIdx.x == 0) {
+    __shared__ double sm[256];
+    if (a.loss_partials) {
+      double s = 0.0;
+      for (int i = threadIdx.x; i < a.n_loss_partials; i += 256) s += (double)a.loss_partials[i];
+      sm[threadIdx.x] = s;
+      __syncthreads();
+      for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) *a.loss_sum_out = sm[0];
+    }
+    if (threadIdx.x == 0 && a.do_finalize) { __threadfence_block(); finalize_scalars_body(fin); }
+    return;
+  }
+  int si = 0;
+  while (si + 1 < a.nseg && (int)blockIdx.x >= a.seg[si + 1].block0) ++si;
+  const GaSeg& sg = a.seg[si];
+  const int lb = blockIdx.x - sg.block0;
+  if (sg.kind == 0) {
+    for (int64_t i = (int64_t)lb * 256 + threadIdx.x; i < sg.count; i += (int64_t)sg.nblocks * 256) {
+      float t = 0.f;
+      for (int s = 0; s < sg.nslices; ++s) t += __ldg(sg.src + (int64_t)s * sg.count + i);
+      a.G[sg.g_off + i] = t;
+    }
+  } else {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int64_t col = (int64_t)lb * 32 + cx;
+    float t = 0.f;
+    if (col < sg.count)
+      for (int g = ry; g < sg.nslices; g += 8) t += __ldg(sg.src + (int64_t)g * sg.count + col);
+    red[ry][cx] = t;
+    __syncthreads();
+    if (ry == 0 && col < sg.count) {
+      float u = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u += red[i][cx];
+      a.G[sg.g_off + col] = u;
+    }
   }
 }
 

@@ -490,6 +490,11 @@ class Engine:
         return self.lib.mmae_graph_replays(self._h)
 
     @property
+    def wgrad_group_launches(self):
+        """How many of the launches were the grouped weight-gradient kernel (every dW of a step in one launch)."""
+        return self.lib.mmae_wgrad_group_launches(self._h)
+
+    @property
     def backward_chain_launches(self):
         """How many of the launches were the whole-backward (all dgrads of a step) kernel."""
         return self.lib.mmae_backward_chain_launches(self._h)
