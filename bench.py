@@ -270,11 +270,9 @@ def main():
         if name == 'infer':
             eng.forward_into(X, filled=filled)
         else:
-            eng.gen_noise(B, rank * B)
-            eng.train_step(X, noise=True, keep=1.0)
+            eng.train_step(X, noise='gen', keep=1.0)          # Philox descriptor drawn inside the step (global rows: set_shard)
             if name == 'cls':
-                eng.gen_noise(B, rank * B)
-                eng.cls_train_step(X, Y, noise=True, keep=1.0)
+                eng.cls_train_step(X, Y, noise='gen', keep=1.0)
 
     def sync_all():
         torch.cuda.synchronize()

@@ -154,7 +154,11 @@ int mmae_apply_noise(mmae_engine* e, const float* X_dev, int64_t batch, float* o
 int mmae_forward(mmae_engine* e, const float* X_dev, const float* target_dev, const float* labels_dev,
                  int64_t batch, int use_noise, float keep, uint32_t want, const mmae_outputs* out);
 
-/* ---- session.run([opt_step]) (:590): forward + backward + Adam on the autoencoder ---- */
+/* ---- session.run([opt_step]) (:590): forward + backward + Adam on the autoencoder ----
+ * use_noise: 0 = X_dev is fed as it is; 1 = apply the descriptor loaded by mmae_set_noise / mmae_gen_noise;
+ * MMAE_NOISE_DRAW (3) = draw this step's Philox descriptor inside the call (add_noise_to_batch, :668-702, fused with
+ * the production of the noisy batch: one kernel instead of a draw pass and an apply pass). */
+#define MMAE_NOISE_DRAW 3
 int mmae_train_step(mmae_engine* e, const float* X_dev, int64_t batch, int use_noise, float keep);
 /* Same step with the two feeds given separately, as feed_dict {noisy_X: ..., true_X: ...} does (:570-571):
  * X_in_dev is what the encoder reads (an already-noised matrix when use_noise == 0), target_dev what the

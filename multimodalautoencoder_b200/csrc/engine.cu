@@ -1092,7 +1092,7 @@ struct mmae_engine {
       if (first_of_var) {
         GaSeg& sg = ga.seg[ga.nseg++];
         sg.g_off = items[q].v->off; sg.count = (int64_t)d.M * d.N; sg.src = P.ws; sg.nslices = pl.splits; sg.kind = 0;
-        sg.block0 = nblk; sg.nblocks = (int)std::min<int64_t>(64, (sg.count + 255) / 256); nblk += sg.nblocks;
+        sg.block0 = nblk; sg.nblocks = (int)std::min<int64_t>(64, (sg.count + GA_THREADS - 1) / GA_THREADS); nblk += sg.nblocks;
       } else {
         ga.seg[ga.nseg - 1].nslices += pl.splits;          // tied: decoder part + encoder part, adjacent slice lists
       }
@@ -1126,7 +1126,7 @@ struct mmae_engine {
     }
     ga.do_finalize = fast_step ? 1 : 0;
     FinalizeArgs fin = finalize_args(B, true, false, fast_step ? 0 : -1, fast_step);
-    grad_assemble_kernel<<<nblk, 256, 0, stream>>>(ga, fin);
+    grad_assemble_kernel<<<nblk, GA_THREADS, 0, stream>>>(ga, fin);
     CKL("grad_assemble");
     if (fast_step) step_finalized = true;
     d_fused = false;
@@ -1362,9 +1362,45 @@ int launch_noise_gen(mmae_engine* e, int64_t batch, int64_t first_row) {
   return 0;
 }
 
-int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float keep, const float* target = nullptr, bool defer_advance = false) {
+// use_noise == 3: draw this step's descriptor inside the call.  On the tcgen05 path one kernel draws it and writes the
+// noisy batch (sample_noise_kernel); elsewhere it is noise_gen_kernel followed by the operand-load application.
+bool noise_materialises(const mmae_engine* e, int64_t B) {
+  return e->cfg.precision == MMAE_PREC_TF32 && B >= 32 && (e->F & 3) == 0 && e->F <= SN_MAX_ZW * 32 &&
+         !const_cast<mmae_engine*>(e)->noise_fusion_on();
+}
+int launch_sample_noise(mmae_engine* e, const float* src, uint32_t n_rows, const int64_t* idx_in, int64_t batch, int64_t first_row,
+                        float* clean_out) {
+  int r = e->ensure_acts(batch); if (r) return r;
+  SampleNoiseArgs a; memset(&a, 0, sizeof(a));
+  a.g.zero_bits = e->zero_bits; a.g.mod_bits = e->mod_bits; a.g.batch = batch; a.g.row0 = first_row;
+  a.g.num_feats = e->F; a.g.zw = (e->F + 31) / 32; a.g.n_zero = e->cfg.n_zero; a.g.num_mod = e->M;
+  a.g.mode = e->cfg.noise_mode; a.g.num_types = (int)e->type_masks.size(); a.g.num_drop = e->cfg.num_modalities_to_drop;
+  for (size_t i = 0; i < e->thresholds.size(); ++i) a.g.thresholds[i] = e->thresholds[i];
+  for (size_t i = 0; i < e->type_masks.size(); ++i) a.g.type_masks[i] = e->type_masks[i];
+  a.g.step = &e->d_state->step; a.g.seed = e->cfg.seed;
+  a.src = src; a.n_rows = n_rows; a.idx_in = idx_in; a.idx_out = n_rows ? e->d_idx : nullptr;
+  a.clean_out = clean_out; a.noisy_out = e->noisy; a.col_mod = e->d_col_mod; a.mask_with = e->cfg.mask_with;
+  const int64_t blocks = std::min<int64_t>((batch + SN_WARPS - 1) / SN_WARPS, (int64_t)e->num_sms * 16);
+  sample_noise_kernel<<<(unsigned)blocks, SN_WARPS * 32, 0, e->stream>>>(a);
+  ++e->launches;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return e->cuda_fail(err, "sample_noise");
+  e->noise_rows = batch;
+  return 0;
+}
+
+int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float keep, const float* target = nullptr, bool defer_advance = false,
+             bool noisy_ready = false) {
+  if (use_noise == 3 && !noisy_ready) {
+    if (e->sticky) return e->fail(MMAE_ERR_CUDA, "engine is in a sticky CUDA error state: " + e->err);
+    int r0 = e->ensure_cap(B); if (r0) return r0;
+    if (noise_materialises(e, B)) { r0 = launch_sample_noise(e, X, 0, nullptr, B, e->first_row, nullptr); noisy_ready = true; }
+    else r0 = launch_noise_gen(e, B, e->first_row);
+    if (r0) return r0;
+  }
   int r = e->begin_step(B, use_noise != 0); if (r) return r;
   mmae_engine::FwdOpts o; o.X = X; o.target = target ? target : X; o.labels = nullptr; o.B = B; o.noise = use_noise != 0; o.keep = keep;
+  o.noisy_ready = noisy_ready;
   o.train_recon = true; o.decoder = true; o.headp = false; o.recon_out = nullptr;
   r = e->forward(o); if (r) return r;
   r = e->sums_allreduce(); if (r) return r;          // overlaps the whole backward pass
@@ -1373,10 +1409,19 @@ int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float kee
   return e->advance_step(!defer_advance);
 }
 
-int do_cls(mmae_engine* e, const float* X, const float* Y, int64_t B, int use_noise, float keep, bool defer_advance = false) {
+int do_cls(mmae_engine* e, const float* X, const float* Y, int64_t B, int use_noise, float keep, bool defer_advance = false,
+           bool noisy_ready = false) {
   if (e->H == 0) return e->fail(MMAE_ERR_STATE, "engine was created without a classification head");
+  if (use_noise == 3 && !noisy_ready) {
+    if (e->sticky) return e->fail(MMAE_ERR_CUDA, "engine is in a sticky CUDA error state: " + e->err);
+    int r0 = e->ensure_cap(B); if (r0) return r0;
+    if (noise_materialises(e, B)) { r0 = launch_sample_noise(e, X, 0, nullptr, B, e->first_row, nullptr); noisy_ready = true; }
+    else r0 = launch_noise_gen(e, B, e->first_row);
+    if (r0) return r0;
+  }
   int r = e->begin_step(B, use_noise != 0); if (r) return r;
   mmae_engine::FwdOpts o; o.X = X; o.target = nullptr; o.labels = Y; o.B = B; o.noise = use_noise != 0; o.keep = keep;
+  o.noisy_ready = noisy_ready;
   o.train_recon = false; o.decoder = false; o.headp = true; o.recon_out = nullptr;
   r = e->forward(o); if (r) return r;
   r = e->head_loss(Y, B, true, nullptr, nullptr); if (r) return r;
@@ -1661,9 +1706,9 @@ int mmae_apply_update(mmae_engine* e, int optimizer) {
 }
 
 namespace {
-int train_core(mmae_engine* e, const float* Xd, const float* target, int64_t batch, int use_noise, float keep) {
+int train_core(mmae_engine* e, const float* Xd, const float* target, int64_t batch, int use_noise, float keep, bool noisy_ready = false) {
   e->fast_step = !e->dp_on(); e->step_finalized = false; e->pending_loss_partials = 0;
-  int r = do_train(e, Xd, batch, use_noise, keep, target, true);
+  int r = do_train(e, Xd, batch, use_noise, keep, target, true, noisy_ready);
   e->fast_step = false;
   if (r) return r;
   r = e->flush_pending_loss(); if (r) return r;
@@ -1671,8 +1716,8 @@ int train_core(mmae_engine* e, const float* Xd, const float* target, int64_t bat
   if (!e->step_finalized) { r = e->finalize_scalars(batch, true, false, 0, true); if (r) return r; }
   return e->apply_update(0, batch, true);
 }
-int cls_core(mmae_engine* e, const float* Xd, const float* Yd, int64_t batch, int use_noise, float keep) {
-  int r = do_cls(e, Xd, Yd, batch, use_noise, keep, true); if (r) return r;
+int cls_core(mmae_engine* e, const float* Xd, const float* Yd, int64_t batch, int use_noise, float keep, bool noisy_ready = false) {
+  int r = do_cls(e, Xd, Yd, batch, use_noise, keep, true, noisy_ready); if (r) return r;
   r = e->allreduce_grads(); if (r) return r;
   r = e->finalize_scalars(batch, false, true, 1, true); if (r) return r;
   return e->apply_update(1, batch, true);
@@ -1685,14 +1730,14 @@ mmae_engine::GraphKey graph_key(mmae_engine* e, int kind, const void* X, const v
 }
 int train_graphed(mmae_engine* e, const float* Xd, const float* target, int64_t batch, int use_noise, float keep) {
   if (e->sticky) return e->fail(MMAE_ERR_CUDA, "engine is in a sticky CUDA error state: " + e->err);
-  if (use_noise && e->noise_rows < batch) return train_core(e, Xd, target, batch, use_noise, keep);   // reports the state error
+  if (use_noise && use_noise != 3 && e->noise_rows < batch) return train_core(e, Xd, target, batch, use_noise, keep);   // reports the state error
   return e->run_graphed(graph_key(e, 0, Xd, nullptr, target, batch, use_noise, keep), 0, batch,
                         [&] { return train_core(e, Xd, target, batch, use_noise, keep); });
 }
 int cls_graphed(mmae_engine* e, const float* Xd, const float* Yd, int64_t batch, int use_noise, float keep) {
   if (e->H == 0) return e->fail(MMAE_ERR_STATE, "engine was created without a classification head");
   if (e->sticky) return e->fail(MMAE_ERR_CUDA, "engine is in a sticky CUDA error state: " + e->err);
-  if (use_noise && e->noise_rows < batch) return cls_core(e, Xd, Yd, batch, use_noise, keep);
+  if (use_noise && use_noise != 3 && e->noise_rows < batch) return cls_core(e, Xd, Yd, batch, use_noise, keep);
   return e->run_graphed(graph_key(e, 1, Xd, Yd, nullptr, batch, use_noise, keep), 1, batch,
                         [&] { return cls_core(e, Xd, Yd, batch, use_noise, keep); });
 }
@@ -1717,8 +1762,8 @@ int mmae_train_step_host(mmae_engine* e, const float* X_host, int64_t batch, int
   ENTER(e);
   float* Xd = nullptr;
   int t = stage_host(e, X_host, nullptr, batch, 0, &Xd, nullptr); if (t < 0) return t;
-  if (gen_noise == 1) { int r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }      // 2: descriptor from mmae_set_noise
-  int r = train_graphed(e, Xd, nullptr, batch, gen_noise ? 1 : 0, keep); if (r) return r;
+  // 1: this step's descriptor is drawn inside the step;  2: descriptor from mmae_set_noise
+  int r = train_graphed(e, Xd, nullptr, batch, gen_noise == 1 ? 3 : (gen_noise ? 1 : 0), keep); if (r) return r;
   return release_stage(e, t);
 }
 
@@ -1728,8 +1773,7 @@ int mmae_cls_train_step_host(mmae_engine* e, const float* X_host, const float* l
   float *Xd = nullptr, *Yd = nullptr;
   const int ycols = e->cfg.head_loss == MMAE_HEAD_SIGMOID_CE ? e->C : 1;
   int t = stage_host(e, X_host, labels_host, batch, ycols, &Xd, &Yd); if (t < 0) return t;
-  if (gen_noise == 1) { int r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }
-  int r = cls_graphed(e, Xd, Yd, batch, gen_noise ? 1 : 0, keep); if (r) return r;
+  int r = cls_graphed(e, Xd, Yd, batch, gen_noise == 1 ? 3 : (gen_noise ? 1 : 0), keep); if (r) return r;
   return release_stage(e, t);
 }
 
@@ -1879,26 +1923,35 @@ int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, 
   // from StepState in device memory, so the whole sequence replays as one graph
   auto body = [&]() -> int {
     cudaError_t ce;
+    const int wpb = 8;
+    bool noisy_ready = false;
     if (idx_host) {
       ce = cudaMemcpyAsync(e->d_idx, idx_host, (size_t)batch * 8, cudaMemcpyHostToDevice, e->stream);
       if (ce != cudaSuccess) return e->cuda_fail(ce, "H2D indices");
-    } else {
-      philox_indices_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, e->stream>>>(e->d_idx, batch, e->first_row,
-                                                                                  (uint32_t)e->ds_rows[slot], &e->d_state->step, e->cfg.seed);
-      ++e->launches;
     }
-    const int wpb = 8;
-    gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_X[slot], e->d_idx, e->gxb, batch, e->F);
-    ++e->launches;
+    if (gen_noise && noise_materialises(e, batch)) {
+      // one kernel: Philox row indices (or the given ones), gather of the clean batch, descriptor, noisy batch
+      int rr = launch_sample_noise(e, e->ds_X[slot], (uint32_t)e->ds_rows[slot], idx_host ? e->d_idx : nullptr, batch, e->first_row, e->gxb);
+      if (rr) return rr;
+      noisy_ready = true;
+    } else {
+      if (!idx_host) {
+        philox_indices_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, e->stream>>>(e->d_idx, batch, e->first_row,
+                                                                                    (uint32_t)e->ds_rows[slot], &e->d_state->step, e->cfg.seed);
+        ++e->launches;
+      }
+      gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_X[slot], e->d_idx, e->gxb, batch, e->F);
+      ++e->launches;
+      if (gen_noise) { int rr = launch_noise_gen(e, batch, e->first_row); if (rr) return rr; }
+    }
     if (classification) {
       gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_Y[slot], e->d_idx, e->gyb, batch, e->ds_ycols[slot]);
       ++e->launches;
     }
     ce = cudaGetLastError();
     if (ce != cudaSuccess) return e->cuda_fail(ce, "gather");
-    if (gen_noise) { int rr = launch_noise_gen(e, batch, e->first_row); if (rr) return rr; }
-    return classification ? cls_core(e, e->gxb, e->gyb, batch, gen_noise ? 1 : 0, keep)
-                          : train_core(e, e->gxb, nullptr, batch, gen_noise ? 1 : 0, keep);
+    return classification ? cls_core(e, e->gxb, e->gyb, batch, gen_noise ? 1 : 0, keep, noisy_ready)
+                          : train_core(e, e->gxb, nullptr, batch, gen_noise ? 1 : 0, keep, noisy_ready);
   };
   if (idx_host || e->sticky) return body();            // host-supplied indices: pageable copy, stay eager
   return e->run_graphed(graph_key(e, 2 + slot * 2 + (classification ? 1 : 0), e->ds_X[slot], e->ds_Y[slot], nullptr, batch, gen_noise ? 1 : 0, keep),

@@ -558,21 +558,22 @@ __device__ __forceinline__ void finalize_scalars_body(const FinalizeArgs& a) {
   }
 }
 
-__global__ void __launch_bounds__(256) grad_assemble_kernel(const GaArgs a, const FinalizeArgs fin) {
+constexpr int GA_THREADS = 1024;
+__global__ void __launch_bounds__(GA_THREADS) grad_assemble_kernel(const GaArgs a, const FinalizeArgs fin) {
   if (blockIdx.x == 0) {
-    __shared__ double sm[256];
+    __shared__ double sm[GA_THREADS];
     if (a.loss_partials) {
       double s = 0.0;
-      for (int i = threadIdx.x; i < a.n_loss_partials; i += 256) s += (double)a.loss_partials[i];
+      for (int i = threadIdx.x; i < a.n_loss_partials; i += GA_THREADS) s += (double)a.loss_partials[i];
       sm[threadIdx.x] = s;
       __syncthreads();
-      for (int o = 128; o > 0; o >>= 1) {
+      for (int o = GA_THREADS / 2; o > 0; o >>= 1) {
         if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
         __syncthreads();
       }
       if (threadIdx.x == 0) *a.loss_sum_out = sm[0];
     }
-    if (threadIdx.x == 0 && a.do_finalize) { __threadfence_block(); finalize_scalars_body(fin); }
+    if (threadIdx.x == 0 && a.do_finalize) finalize_scalars_body(fin);
     return;
   }
   int si = 0;
@@ -580,24 +581,35 @@ __global__ void __launch_bounds__(256) grad_assemble_kernel(const GaArgs a, cons
   const GaSeg& sg = a.seg[si];
   const int lb = blockIdx.x - sg.block0;
   if (sg.kind == 0) {
-    for (int64_t i = (int64_t)lb * 256 + threadIdx.x; i < sg.count; i += (int64_t)sg.nblocks * 256) {
+    for (int64_t i = (int64_t)lb * GA_THREADS + threadIdx.x; i < sg.count; i += (int64_t)sg.nblocks * GA_THREADS) {
       float t = 0.f;
+#pragma unroll 6
       for (int s = 0; s < sg.nslices; ++s) t += __ldg(sg.src + (int64_t)s * sg.count + i);
       a.G[sg.g_off + i] = t;
     }
   } else {
-    __shared__ float red[8][33];
+    // 32 columns x 32 row lanes; each lane walks its groups 8 loads at a time, then a fixed-order tree over the lanes
+    __shared__ float red[32][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int64_t col = (int64_t)lb * 32 + cx;
     float t = 0.f;
-    if (col < sg.count)
-      for (int g = ry; g < sg.nslices; g += 8) t += __ldg(sg.src + (int64_t)g * sg.count + col);
+    if (col < sg.count) {
+      int g = ry;
+      for (; g + 7 * 32 < sg.nslices; g += 8 * 32) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(sg.src + (int64_t)(g + u * 32) * sg.count + col);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t += v[u];
+      }
+      for (; g < sg.nslices; g += 32) t += __ldg(sg.src + (int64_t)g * sg.count + col);
+    }
     red[ry][cx] = t;
     __syncthreads();
     if (ry == 0 && col < sg.count) {
       float u = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) u += red[i][cx];
+      for (int i = 0; i < 32; ++i) u += red[i][cx];
       a.G[sg.g_off + col] = u;
     }
   }

@@ -315,22 +315,28 @@ class Engine:
                                        C.c_void_p(tgt.data_ptr()) if tgt is not None else None, None,
                                        X.shape[0], 0, 1.0, want, C.byref(o)))
 
+    @staticmethod
+    def _noise_flag(noise):
+        """False: no noise;  True: apply the descriptor loaded by set_noise / gen_noise;  'gen': draw this step's Philox
+        descriptor inside the call (one kernel draws it and writes the noisy batch)."""
+        return 3 if noise == 'gen' else int(bool(noise))
+
     def train_step(self, X, noise=False, keep=1.0):
         X = self._dev(X)
-        self._ck(self.lib.mmae_train_step(self._h, C.c_void_p(X.data_ptr()), X.shape[0], int(bool(noise)), float(keep)))
+        self._ck(self.lib.mmae_train_step(self._h, C.c_void_p(X.data_ptr()), X.shape[0], self._noise_flag(noise), float(keep)))
 
     def train_step_pair(self, X_in, target, noise=False, keep=1.0):
         X_in = self._dev(X_in)
         target = self._dev(target)
         self._ck(self.lib.mmae_train_step_pair(self._h, C.c_void_p(X_in.data_ptr()), C.c_void_p(target.data_ptr()),
-                                               X_in.shape[0], int(bool(noise)), float(keep)))
+                                               X_in.shape[0], self._noise_flag(noise), float(keep)))
 
     def cls_train_step(self, X, Y, noise=False, keep=1.0):
         X = self._dev(X)
         self._check_labels(Y, X.shape[0])
         Y = self._dev(Y)
         self._ck(self.lib.mmae_cls_train_step(self._h, C.c_void_p(X.data_ptr()), C.c_void_p(Y.data_ptr()),
-                                              X.shape[0], int(bool(noise)), float(keep)))
+                                              X.shape[0], self._noise_flag(noise), float(keep)))
 
     def train_step_host(self, X_host, gen_noise=False, keep=1.0, use_noise=False):
         """X_host: C-contiguous float32 ndarray or pinned CPU tensor (kept alive by the caller until synchronize()).

@@ -200,3 +200,32 @@ def test_backward_chain_matches_oracle_and_layerwise(case):
         want = G[name] - l2 * P[name]                           # the engine folds L2 into Adam
         assert np.linalg.norm(gc * scale - want) <= 5e-3 * max(np.linalg.norm(want), 1e-30), name
     ec.close(); el.close()
+
+
+@pytest.mark.parametrize('prec', ['tf32', 'fp32'])
+def test_noise_drawn_inside_the_step_equals_draw_then_apply(prec):
+    """noise='gen' (sample_noise_kernel: descriptor + noisy batch in one pass) is bit-identical to gen_noise followed by
+    a step that applies the stored descriptor: same descriptor bytes, same loss, same gradients."""
+    from multimodalautoencoder_b200 import Engine
+    ocfg, ecfg = make_cfgs(precision=prec, tie=False, seed=9)
+    B = 777
+    rng = np.random.default_rng(3)
+    X = rng.uniform(0, 1, (B, 320)).astype(np.float32)
+    P = O.init_params(ocfg, rng)
+    runs = []
+    for mode in ('two', 'one'):
+        e = Engine(ecfg)
+        e.set_params({k: v.astype(np.float32) for k, v in P.items()})
+        e.set_rng_step(5)
+        if mode == 'two':
+            e.gen_noise(B)
+            e.train_step(X, noise=True)
+        else:
+            e.train_step(X, noise='gen')
+        zb, mb = e.get_noise(B)
+        runs.append((zb, mb, e.scalars()['recon_loss'], {n: e.get_gradient(n) for n, _ in e.variables()}))
+        e.close()
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    assert runs[0][2] == runs[1][2]
+    for n in runs[0][3]:
+        assert np.array_equal(runs[0][3][n], runs[1][3][n]), n
