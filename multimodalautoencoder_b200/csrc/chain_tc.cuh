@@ -91,19 +91,6 @@ struct ChainLayer {
 
 inline int ch_round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// plain-fp32 2-D map with [32 x 32] boxes (epilogue loads / stores; TMA clips rows and columns out of range)
-inline bool make_tmap_io(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, int64_t ld) {
-  PFN_encodeTiled enc = get_encode_fn();
-  if (!enc) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, 32};
-  cuuint32_t estr[2] = {1, 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // Fills `p` for X[M, K0] (row stride ldx) pushed through `layers`.  Returns false when the chain does not fit the
 // kernel (TMEM columns, alignment); the caller then uses the per-layer GEMMs.
 inline bool chain_build(ChainParams& p, const float* X, int64_t M, int64_t ldx, const std::vector<ChainLayer>& layers) {

@@ -53,6 +53,8 @@ struct TcParams {
   Epilogue ep;
   NoiseView nz;                 // two-SM kernel only: block-mask + zero noise applied to the A tile in shared memory
   int nz_aligned;               // every modality boundary is a multiple of 32 columns (one modality per 32-column chunk)
+  CUtensorMap tmC;              // two-SM kernel only: [32 x 32] boxes over C for the row-layout TMA-store epilogue
+  int tma_epi;                  // 1: bias/act, dgrad and loss epilogues keep thread = row and leave through tmC
 };
 
 // ------------------------------------------------------------------ host side
@@ -110,6 +112,19 @@ inline bool make_tmap_mn3d(CUtensorMap* tm, const float* base, int64_t k_rows, i
                    const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+// plain-fp32 2-D map with [32 x 32] boxes (epilogue loads / stores; TMA clips rows and columns out of range)
+inline bool make_tmap_io(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 inline bool tc_gemm_eligible(bool ta, bool tb, const GemmArgs& g, bool allow_noise = false) {
@@ -253,6 +268,21 @@ inline cudaError_t launch_gemm_tc2(bool ta, bool tb, const GemmArgs& g, const Tc
     p.C = g.C; p.ldc = g.ldc; p.split_stride = 0;
   }
   p.nz = g.noise; p.nz_aligned = g.noise_aligned32;
+  // Row-layout epilogue: thread = accumulator row, 16-byte shared-memory stores into a 128B-swizzled tile, one TMA store per
+  // 32 x 32 chunk, auxiliary operand (loss target / saved activation) read as 16-byte global loads issued before the
+  // accumulator is awaited.  A third of the memory instructions of the column-per-lane epilogue it replaces, which
+  // bounded the dgrad and the K = 256 launches of the wide step.
+  static int tma_epi_on = -1;
+  if (tma_epi_on < 0) { const char* ev = getenv("MMAE_TMA_EPI"); tma_epi_on = (ev && ev[0] == '0') ? 0 : 1; }
+  p.tma_epi = 0;
+  if (tma_epi_on && !a_mn && !b_mn && !g.noise.enabled && pl.splits == 1 && p.ep.mode != EPI_PLAIN && p.ep.beta == 0.f &&
+      p.ep.keep >= 1.f && (g.N & 3) == 0) {
+    int64_t ldaux = 0; const float* auxp = nullptr;
+    if (p.ep.mode == EPI_LOSS_TRAIN || p.ep.mode == EPI_LOSS_PRED) { auxp = p.ep.target; ldaux = p.ep.ldt; }
+    else if (p.ep.mode == EPI_DGRAD) { auxp = p.ep.saved; ldaux = p.ep.lds; }
+    const bool aux_ok = !auxp || ((ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(auxp) & 15) == 0);
+    if (aux_ok && make_tmap_io(&p.tmC, p.C, g.M, g.N, p.ldc)) p.tma_epi = 1;
+  }
   return tc2_launch(a_mn, b_mn, g.noise.enabled != 0, p, pl.grid, st);
 }
 

@@ -27,6 +27,7 @@ constexpr int TC2_STAGE_BYTES = TC2_ABYTES + TC2_BBYTES;
 constexpr int TC2_EPI_BYTES = TC_EPI_WARPS * 32 * TC_STAGE_LD * 4;
 constexpr int TC2_BAR_BYTES = 512;
 constexpr int TC2_SMEM = TC2_STAGES * TC2_STAGE_BYTES + TC2_EPI_BYTES + 1024 + TC2_BAR_BYTES;
+static_assert(TC2_EPI_BYTES % 1024 == 0, "barriers follow the staging region");
 static_assert(TC2_SMEM <= 232448, "two-SM GEMM shared memory exceeds the per-CTA limit");
 constexpr int TC2_THREADS_NOISE = TC_THREADS + 128;      // + 4 warps that apply the mask / noise to the A tile in shared memory
 constexpr int TC2_PATCH_WARP0 = TC_THREADS / 32;
@@ -91,6 +92,158 @@ __device__ __forceinline__ void patch_row32(const NoiseView& nz, int aligned, ui
   }
 }
 
+
+// ------------------------------------------------------------------ row-layout epilogue (thread = accumulator row)
+__device__ __forceinline__ uint32_t rt_chunk(uint32_t tile_saddr, int lane, int q) { return tile_saddr + lane * 128 + ((q ^ (lane & 7)) << 4); }
+__device__ __forceinline__ void rt_sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void rt_tma_store(const CUtensorMap* tm, uint32_t src_saddr, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src_saddr), "r"(c0), "r"(c1) : "memory");
+}
+struct RtAux { float4 v[8]; };
+// Auxiliary values (loss target / saved activation) of the 32 x 32 chunk at (row0, col0), COALESCED: load i of lane l
+// covers row row0 + l/8 + 4i, columns col0 + 4 (l%8) .. +3, so every instruction reads four full 128-byte row segments.
+// The values reach the row-per-thread layout through the warp's shared-memory tile (rt_stage_aux).
+__device__ __forceinline__ void rt_load_aux(const float* auxp, int64_t ldaux, int64_t row0, int64_t M, int64_t col0, int64_t N, int lane, RtAux& ax) {
+  const int q = lane & 7;
+  const bool col_ok = auxp != nullptr && col0 + q * 4 < N;
+  const float* sp = auxp + col0 + q * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t row = row0 + (lane >> 3) + 4 * i;
+    if (col_ok && row < M)
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(ax.v[i].x), "=f"(ax.v[i].y), "=f"(ax.v[i].z), "=f"(ax.v[i].w) : "l"(sp + row * ldaux));
+    else ax.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ float4 rt_lds128(uint32_t a) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+// coalesced-load layout -> this thread's row (through the 128B-swizzled tile; conflict-free both ways)
+__device__ __forceinline__ void rt_stage_aux(uint32_t tile_s, int lane, RtAux& ax) {
+  const int q = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = (lane >> 3) + 4 * i;
+    rt_sts128(tile_s + rr * 128 + ((q ^ (rr & 7)) << 4), ax.v[i]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ax.v[j] = rt_lds128(rt_chunk(tile_s, lane, j));
+}
+// column sums over the 32 rows (lanes) of a chunk held one row per lane: transposing butterfly, 31 shuffles, fixed
+// summation tree; lane l returns the sum of column l
+__device__ __forceinline__ float rt_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { const bool up = lane & 16; const float send = up ? v[j] : v[j + 16]; const float keep = up ? v[j + 16] : v[j]; v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const bool up = lane & 8; const float send = up ? v[j] : v[j + 8]; const float keep = up ? v[j + 8] : v[j]; v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const bool up = lane & 4; const float send = up ? v[j] : v[j + 4]; const float keep = up ? v[j + 4] : v[j]; v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) { const bool up = lane & 2; const float send = up ? v[j] : v[j + 2]; const float keep = up ? v[j + 2] : v[j]; v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2); }
+  { const bool up = lane & 1; const float send = up ? v[0] : v[1]; const float keep = up ? v[1] : v[0]; v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1); }
+  return v[0];
+}
+
+// One 32 x 32 chunk: r = this row's accumulators.  MODE / SUB / DROP as in epi_rows (gemm_tc_kernel.cuh).
+template <int MODE, int SUB, bool DROP>
+__device__ __forceinline__ void rt_chunk_apply(const Epilogue& ep, const uint32_t (&r)[32], const RtAux& ax, int64_t col0, int64_t N,
+                                               int64_t grow, bool row_valid, uint32_t tile_s, int lane, float& loss_acc, float* colsum_row) {
+  constexpr bool kLoss = (MODE == EPI_LOSS_TRAIN || MODE == EPI_LOSS_PRED);
+  const bool has_t = kLoss && ep.target != nullptr;
+  float outv[32];
+  float lsum = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool col_ok = col0 + q * 4 < N;
+    if ((MODE == EPI_BIAS_ACT || kLoss) && ep.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q);     // warp-uniform: broadcast
+    const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
+    const float as[4] = {ax.v[q].x, ax.v[q].y, ax.v[q].z, ax.v[q].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float acc = __uint_as_float(r[q * 4 + e]);
+      float out;
+      if (MODE == EPI_BIAS_ACT) {
+        out = act_fast_t<SUB>(acc + bs[e]);
+        if (DROP) {
+          uint32_t w = philox_word((uint64_t)grow * (uint64_t)ep.drop_width + (uint64_t)(col0 + q * 4 + e), ep.drop_stream, __ldg(ep.step), ep.seed);
+          out = ((w >> 8) < ep.keep_thr) ? out / ep.keep : 0.f;
+        }
+      } else if (MODE == EPI_DGRAD) {
+        float g = acc, h = as[e];
+        if (DROP) {
+          uint32_t w = philox_word((uint64_t)grow * (uint64_t)ep.drop_width + (uint64_t)(col0 + q * 4 + e), ep.drop_stream, __ldg(ep.step), ep.seed);
+          if ((w >> 8) < ep.keep_thr) { g = g / ep.keep; h = h * ep.keep; } else { g = 0.f; }
+        }
+        out = g * dact_t<SUB>(h);
+      } else {
+        const float l = acc + bs[e], x = as[e];
+        float lv;
+        if (SUB == MMAE_LOSS_SIGMOID_CE) {
+          const float ee = __expf(-fabsf(l));
+          const float inv = __fdividef(1.f, 1.f + ee);
+          const float sg = l >= 0.f ? inv : ee * inv;
+          lv = fmaxf(l, 0.f) - l * x + __logf(1.f + ee);
+          out = (MODE == EPI_LOSS_TRAIN) ? (sg - x) : sg;
+        } else if (SUB == MMAE_LOSS_RMSE) {
+          const float d = l - x;
+          lv = d * d;
+          out = (MODE == EPI_LOSS_TRAIN) ? d : l;
+        } else {
+          lv = -x * __logf(l);
+          out = (MODE == EPI_LOSS_TRAIN) ? __fdividef(-x, l) : l;
+        }
+        if (has_t && col_ok) lsum += lv;
+      }
+      outv[q * 4 + e] = out;
+    }
+    rt_sts128(rt_chunk(tile_s, lane, q), make_float4(outv[q * 4], outv[q * 4 + 1], outv[q * 4 + 2], outv[q * 4 + 3]));
+  }
+  if (has_t && row_valid) loss_acc += lsum;
+  if (colsum_row) {            // bias gradient: column sums of the stored values over this chunk's rows inside M
+    if (!row_valid) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) outv[j] = 0.f;
+    }
+    const float cs = rt_colsum32(outv, lane);
+    if (col0 + lane < N) colsum_row[col0 + lane] = cs;
+  }
+}
+template <int MODE, bool DROP>
+__device__ __forceinline__ void rt_dispatch_act(const Epilogue& ep, const uint32_t (&r)[32], const RtAux& ax, int64_t col0, int64_t N, int64_t grow,
+                                                bool row_valid, uint32_t tile_s, int lane, float& loss_acc, float* colsum_row) {
+  switch (ep.act) {
+    case MMAE_ACT_RELU: rt_chunk_apply<MODE, MMAE_ACT_RELU, DROP>(ep, r, ax, col0, N, grow, row_valid, tile_s, lane, loss_acc, colsum_row); break;
+    case MMAE_ACT_TANH: rt_chunk_apply<MODE, MMAE_ACT_TANH, DROP>(ep, r, ax, col0, N, grow, row_valid, tile_s, lane, loss_acc, colsum_row); break;
+    case MMAE_ACT_SOFTSIGN: rt_chunk_apply<MODE, MMAE_ACT_SOFTSIGN, DROP>(ep, r, ax, col0, N, grow, row_valid, tile_s, lane, loss_acc, colsum_row); break;
+    case MMAE_ACT_SOFTPLUS: rt_chunk_apply<MODE, MMAE_ACT_SOFTPLUS, DROP>(ep, r, ax, col0, N, grow, row_valid, tile_s, lane, loss_acc, colsum_row); break;
+    default: rt_chunk_apply<MODE, MMAE_ACT_LINEAR, DROP>(ep, r, ax, col0, N, grow, row_valid, tile_s, lane, loss_acc, colsum_row); break;
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void rt_dispatch_loss(const Epilogue& ep, const uint32_t (&r)[32], const RtAux& ax, int64_t col0, int64_t N, int64_t grow,
+                                                 bool row_valid, uint32_t tile_s, int lane, float& loss_acc, float* colsum_row) {
+  switch (ep.loss) {
+    case MMAE_LOSS_SIGMOID_CE: rt_chunk_apply<MODE, MMAE_LOSS_SIGMOID_CE, false>(ep, r, ax, col0, N, grow, row_valid, tile_s, lane, loss_acc, colsum_row); break;
+    case MMAE_LOSS_RMSE: rt_chunk_apply<MODE, MMAE_LOSS_RMSE, false>(ep, r, ax, col0, N, grow, row_valid, tile_s, lane, loss_acc, colsum_row); break;
+    default: rt_chunk_apply<MODE, MMAE_LOSS_CE, false>(ep, r, ax, col0, N, grow, row_valid, tile_s, lane, loss_acc, colsum_row); break;
+  }
+}
+__device__ __forceinline__ void rt_dispatch(const Epilogue& ep, const uint32_t (&r)[32], const RtAux& ax, int64_t col0, int64_t N, int64_t grow,
+                                            bool row_valid, uint32_t tile_s, int lane, float& loss_acc, float* colsum_row) {
+  // (dropout steps keep the column-per-lane epilogue: the host side leaves tma_epi off when keep < 1)
+  switch (ep.mode) {
+    case EPI_BIAS_ACT: rt_dispatch_act<EPI_BIAS_ACT, false>(ep, r, ax, col0, N, grow, row_valid, tile_s, lane, loss_acc, colsum_row); break;
+    case EPI_DGRAD: rt_dispatch_act<EPI_DGRAD, false>(ep, r, ax, col0, N, grow, row_valid, tile_s, lane, loss_acc, colsum_row); break;
+    case EPI_LOSS_TRAIN: rt_dispatch_loss<EPI_LOSS_TRAIN>(ep, r, ax, col0, N, grow, row_valid, tile_s, lane, loss_acc, colsum_row); break;
+    default: rt_dispatch_loss<EPI_LOSS_PRED>(ep, r, ax, col0, N, grow, row_valid, tile_s, lane, loss_acc, colsum_row); break;
+  }
+}
+
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -99,7 +252,8 @@ template <bool A_MN, bool B_MN, bool NOISE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NOISE ? TC2_THREADS_NOISE : TC_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC2_STAGES * TC2_STAGE_BYTES);
+  uint8_t* epi_smem = smem + TC2_STAGES * TC2_STAGE_BYTES;                  // 1024-byte aligned (TMA-store tiles are 128B-swizzled)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + TC2_EPI_BYTES);
   uint64_t* full_bar = bars;                          // [TC2_STAGES]  (the leader's is the one that counts)
   uint64_t* empty_bar = bars + TC2_STAGES;            // [TC2_STAGES]
   uint64_t* tfull_bar = bars + 2 * TC2_STAGES;        // [2]
@@ -282,18 +436,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NOISE ? TC2_THREADS_
     }
   } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_EPI_WARPS) {
     // ===================== epilogue warps (8 per CTA): this CTA's 128 rows, all 256 columns =====================
+    constexpr bool kRowEpi = !A_MN && !B_MN && !NOISE;      // forward / dgrad GEMMs (K-major operands); wgrads are EPI_PLAIN
     const int quad = warp & 3;
     const int half = (warp - TC_EPI_WARP0) >> 2;
-    float* stg = reinterpret_cast<float*>(smem + TC2_STAGES * TC2_STAGE_BYTES + TC2_BAR_BYTES) + (warp - TC_EPI_WARP0) * 32 * TC_STAGE_LD;
+    float* stg = reinterpret_cast<float*>(epi_smem) + (warp - TC_EPI_WARP0) * 32 * TC_STAGE_LD;
+    const uint32_t tile_s = smem_u32(epi_smem) + (uint32_t)(warp - TC_EPI_WARP0) * 4096u;
     float loss_acc = 0.f;
     int64_t ldaux; const float* auxp = epilogue_aux_ptr(p.ep, &ldaux);
     int64_t it = 0;
     for (int64_t t = pair; t < num_tiles; t += num_pairs, ++it) {
       int mb, nb, sp; decode(t, mb, nb, sp);
       const int as = (int)(it & 1); const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+      const int64_t row0 = (int64_t)mb * 256 + (int64_t)rank * TC_BM + quad * 32;
+      if (kRowEpi && p.tma_epi) {
+        // ---- row-layout epilogue: thread = row; the first chunk's auxiliary loads travel while the MMAs still run
+        const int64_t row = row0 + lane;
+        const bool row_valid = row < p.M;
+        const int64_t ncol0 = (int64_t)nb * TC2_BN;
+        RtAux ax;
+        rt_load_aux(auxp, ldaux, row0, p.M, ncol0 + half * 32, p.N, lane, ax);
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = half; ch < TC2_BN / 32; ch += 2) {
+          const int64_t col0 = ncol0 + ch * 32;
+          if (col0 >= p.N || row0 >= p.M) break;                        // warp-uniform: the rest of the tile is outside the matrix
+          uint32_t r[32];
+          tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TC2_BN + ch * 32), r);
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous store has read the tile
+          __syncwarp();
+          if (auxp) rt_stage_aux(tile_s, lane, ax);
+          float* cs_row = p.ep.colsum_partials ? p.ep.colsum_partials + (row0 >> 5) * p.N : nullptr;
+          rt_dispatch(p.ep, r, ax, col0, p.N, row + p.ep.row0, row_valid, tile_s, lane, loss_acc, cs_row);
+          if (ch + 2 < TC2_BN / 32) rt_load_aux(auxp, ldaux, row0, p.M, col0 + 64, p.N, lane, ax);   // next chunk's aux, behind this chunk's store
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) { rt_tma_store(&p.tmC, tile_s, (int)col0, (int)row0); asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+        continue;
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int64_t row0 = (int64_t)mb * 256 + (int64_t)rank * TC_BM + quad * 32;
       float* cbase = p.C + (int64_t)sp * p.split_stride;
 #pragma unroll 1
       for (int ch = half; ch < TC2_BN / 32; ch += 2) {
@@ -320,6 +506,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NOISE ? TC2_THREADS_
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);     // 16 arrivals (both CTAs) free the accumulator stage
     }
+    if (kRowEpi && p.tma_epi && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every output tile has landed
     if (p.ep.loss_partials) {
       float w = warp_sum(loss_acc);
       if (lane == 0) epi_red[warp - TC_EPI_WARP0] = w;
