@@ -289,7 +289,7 @@ def main():
     # The wide workload is timed with per-launch CUDA events on (profiling) inside the timed region.  The small-batch
     # workloads replay a captured CUDA graph per step, which per-launch events would break up: they are timed
     # un-instrumented, and the kernel times for the roofline come from a second, instrumented pass of the same steps.
-    live_profile = name in ('wide', 'infer')
+    live_profile = name in ('wide', 'infer') and world == 1      # (multi-GPU steps replay CUDA graphs at small per-rank batches)
     if live_profile:
         eng.set_profiling(True)
     l0, c0, g0 = eng.kernel_launches, eng.chain_launches, eng.graph_replays

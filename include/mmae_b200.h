@@ -192,9 +192,21 @@ int mmae_apply_update(mmae_engine* e, int optimizer);
 /* ---- device-resident dataset + on-device batch sampling (data_funcs.py:161-195) ---- */
 int mmae_set_dataset(mmae_engine* e, int slot, const float* X_host, const float* Y_host,
                      int64_t rows, int32_t label_cols);
+/* A training VIEW of a resident dataset: the rows a cross-validation fold trains on (set_to_cross_validation_fold,
+ * data_funcs.py:278-308) as a list of dataset rows.  The dataset is uploaded once; switching folds uploads count indices
+ * instead of the matrix.  Sampled / given indices then address the view (index j = dataset row rows_host[j]).
+ * rows_host == NULL clears the view. */
+int mmae_set_dataset_view(mmae_engine* e, int slot, const int64_t* rows_host, int64_t count);
+
 /* idx_host == NULL draws rows from Philox; otherwise the caller's indices (np.random.choice). */
 int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, int64_t batch,
                              int gen_noise, float keep, int classification);
+
+/* ---- get_reconstruction_loss_per_modality (:1189-1216) as one batched pass: for every modality m the rows are
+ *      reconstructed with block m set to the literal -1.0 (:1203) and rmse_host[m] receives sqrt(mean((X - X_hat)^2)) over
+ *      that block's columns.  The M masked copies are stacked into one batch per chunk of rows (one forward for all
+ *      modalities), the squared errors are reduced on the device; X_host is [rows, num_feats] fp32. ---- */
+int mmae_modality_rmse(mmae_engine* e, const float* X_host, int64_t rows, double* rmse_host);
 
 /* ---- scalars of the last call ---- */
 int mmae_read_scalars(mmae_engine* e, double* out, int count);

@@ -112,9 +112,13 @@ class MMAEWrapper(Wrapper):
         from sklearn.svm import SVC
         assert len(self.model.val_loss) > 0, "Model needs to be trained before embeddings can be tested"
         m, cdl = self.model, self.classification_data_loader
-        run = lambda X: m.session.run(m.embedding, {m.noisy_X: X, m.tf_dropout_prob: 1.0})
-        emb_train, emb_val = run(cdl.train_X), run(cdl.val_X)
-        emb_clean, emb_noisy = run(cdl.clean_val_X), run(cdl.noisy_val_X)
+        # ONE embedding pass for the four row sets (the reference ran four session.run calls, autoencoder_wrapper.py:
+        # 212-226): the rows are stacked, encoded once through the TensorFlow-handle shim, and split again.  Row-wise
+        # results do not depend on what else is in the batch (a VAE's epsilon is the only batch-indexed draw).
+        parts = [np.asarray(a, np.float64) for a in (cdl.train_X, cdl.val_X, cdl.clean_val_X, cdl.noisy_val_X)]
+        emb_all = m.session.run(m.embedding, {m.noisy_X: np.concatenate(parts, axis=0), m.tf_dropout_prob: 1.0})
+        cuts = np.cumsum([len(a) for a in parts])[:-1]
+        emb_train, emb_val, emb_clean, emb_noisy = np.split(emb_all, cuts, axis=0)
         n = len(LABELS_TO_PREDICT)
         best = np.zeros((6, n))
         sets = ((emb_val, cdl.val_Y), (emb_noisy, cdl.noisy_val_Y), (emb_clean, cdl.clean_val_Y))

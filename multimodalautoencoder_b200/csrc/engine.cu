@@ -150,6 +150,8 @@ struct mmae_engine {
   // ---- resident datasets
   float* ds_X[2] = {nullptr, nullptr}; float* ds_Y[2] = {nullptr, nullptr};
   int64_t ds_rows[2] = {0, 0}; int ds_ycols[2] = {0, 0};
+  int64_t* ds_view[2] = {nullptr, nullptr}; int64_t ds_view_rows[2] = {0, 0};     // training view (cross-validation fold) as a row list
+  int64_t* d_idx_in = nullptr; int64_t idx_in_cap = 0;
 
   // ---- NCCL: gradient buckets are all-reduced on comm_stream while backward keeps running on `stream`
   void* comm = nullptr; int world = 1, rank = 0;
@@ -452,7 +454,8 @@ struct mmae_engine {
     clear_graphs();
     fr(d_state); fr(PT); fr(colpart); fr(P); fr(G); fr(M0); fr(V0); fr(M1); fr(V1); fr(d_scalars); fr(d_sums); fr(d_segs[0]); fr(d_segs[1]);
     fr(d_col_mod); fr(d_starts); fr(zero_bits); fr(mod_bits); fr(miss_bits);
-    for (int i = 0; i < 2; ++i) { fr(xin[i]); fr(yin[i]); fr(ds_X[i]); fr(ds_Y[i]); }
+    for (int i = 0; i < 2; ++i) { fr(xin[i]); fr(yin[i]); fr(ds_X[i]); fr(ds_Y[i]); fr(ds_view[i]); }
+    fr(d_idx_in);
     fr(noisy); fr(gxb); fr(gyb); fr(wg_ws);
     for (auto q : dch) fr(q); for (auto q : cpch) fr(q);
     for (auto p : ea) fr(p); for (auto p : da) fr(p); for (auto p : ha) fr(p);
@@ -472,6 +475,7 @@ struct mmae_engine {
     if (comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(comm); comm = nullptr; }
     for (auto ev : comm_events) cudaEventDestroy(ev);
     if (comm_done) cudaEventDestroy(comm_done);
+    if (adam_gate) cudaEventDestroy(adam_gate);
     if (comm_stream) cudaStreamDestroy(comm_stream);
   }
 
@@ -553,7 +557,10 @@ struct mmae_engine {
       if (nv.enabled && !two_sm) return fail(MMAE_ERR_STATE, "internal: noisy operand reached the one-SM tcgen05 GEMM");
       if (nv.enabled) ++fused_noise_launches;
       const int max_s = allow_splitk && ep.mode == EPI_PLAIN ? 64 : 1;
-      TcPlan pl = two_sm ? tc2_plan(g, num_sms, max_s) : tc_plan(g, num_sms, max_s);
+      // While gradient buckets are being all-reduced, NCCL's CTAs hold SMs of their own (they cannot share one with a
+      // 227 KB GEMM CTA); a persistent grid sized for all 148 SMs would then need a second wave for its last CTAs.
+      const int sms_eff = comm_busy() ? std::max(2, (num_sms - comm_reserve) & ~1) : num_sms;
+      TcPlan pl = two_sm ? tc2_plan(g, sms_eff, max_s) : tc_plan(g, sms_eff, max_s);
       if (pl.splits > 1) RET(ensure_splitk((int64_t)pl.splits * m * n));
       int pr = prof_begin(2.0 * (double)m * (double)n * (double)k);
       if (pr >= 0) { auto& R = prof_recs[pr]; R.m = m; R.n = n; R.k = k; R.ta = ta; R.tb = tb; R.splits = pl.splits; }
@@ -667,7 +674,8 @@ struct mmae_engine {
   }
   bool graphs_allowed() {
     if (graph_mode < 0) { const char* ev = getenv("MMAE_GRAPHS"); graph_mode = (ev && ev[0] == '0') ? 0 : 1; }
-    return graph_mode == 1 && !profiling && !dp_on() && !sticky;
+    static const bool dp_graphs = !(getenv("MMAE_DP_GRAPHS") && getenv("MMAE_DP_GRAPHS")[0] == '0');
+    return graph_mode == 1 && !profiling && (!dp_on() || dp_graphs) && !sticky;
   }
   template <class Body> int run_graphed(const GraphKey& key, int opt, int64_t B, Body body) {
     if (!graphs_allowed() || B * (int64_t)F > ((int64_t)1 << 26)) return body();      // large batches are not launch-bound
@@ -954,7 +962,7 @@ struct mmae_engine {
       // the NCCL kernels running beside them take SMs away.)
       RET(gemm(true, false, din, dout, B, a_in, din, d, dout, gvar(wn), dout, nv, ew, nullptr, true));
       RET(bucket_vars(wn, bn));
-      if (i == 0) break;
+      if (i == 0) { RET(release_adam()); break; }
       const bool var_here = cfg.variational && i == L - 1;
       Epilogue ed = epi(var_here ? EPI_PLAIN : EPI_DGRAD);
       if (!var_here) { ed.saved = ea[i - 1]; ed.lds = din; ed.act = cfg.activation; if (keep < 1.f) set_dropout(ed, keep, (uint32_t)(i - 1), din); ed.colsum_partials = colpart; }
@@ -971,6 +979,7 @@ struct mmae_engine {
         RET(gemm(false, true, B, din, E, glv, E, pvar("variance_weights"), E, other, din, noise_view(false), e2, nullptr, false));
         d_fused = last_gemm_tc;
       }
+      RET(release_adam());          // the dgrads that read this layer's weights are enqueued: their update may follow the all-reduce
       std::swap(d, other);
     }
     return 0;
@@ -1153,6 +1162,7 @@ struct mmae_engine {
         RET(gemm(true, false, din, dout, B, u_in, din, d, dout, gvar(wn), dout, noise_view(false), ew, nullptr, true));
         RET(bucket_vars(wn, bn));
       }
+      RET(release_adam());          // (every dgrad already ran in the chain launch)
     }
     for (int i = L - 1; i >= 0; --i) {
       const int din = enc_in(i), dout = layers[i];
@@ -1164,6 +1174,7 @@ struct mmae_engine {
       Epilogue ew = epi(EPI_PLAIN); ew.beta = cfg.tie_weights ? 1.f : 0.f;
       RET(gemm(true, false, din, dout, B, a_in, din, dch[k], dout, gvar(wn), dout, nv, ew, nullptr, true));
       RET(bucket_vars(wn, bn));
+      RET(release_adam());
     }
     d_fused = false;
     return 0;
@@ -1196,6 +1207,7 @@ struct mmae_engine {
                noise_view(false), ed, nullptr, false));
       d_fused = last_gemm_tc;
       if (cfg.tie_weights) RET(bucket_vars(bn, bn)); else RET(bucket_vars(wn, bn));   // this decoder layer's gradients are final
+      RET(release_adam());
       d = nxt; ldd = din; nxt = (nxt == dA) ? dB : dA;
     }
     if (cfg.variational) {
@@ -1232,6 +1244,7 @@ struct mmae_engine {
       ed.colsum_partials = colpart;
       RET(gemm(false, true, B, din, dout, d, ldd, pvar(wn), dout, nxt, din, noise_view(false), ed, nullptr, false));
       d_fused = last_gemm_tc;
+      RET(release_adam());
       d = nxt; ldd = din; nxt = (nxt == dA) ? dB : dA;
     }
     if (cfg.variational) {
@@ -1251,6 +1264,18 @@ struct mmae_engine {
   }
   bool dp_on() const { return comm != nullptr && world > 1; }
 
+  // ---- data-parallel pipeline: per-bucket all-reduce, then that bucket's Adam + shadow refresh, all on comm_stream
+  // while backward keeps running on `stream`.  Only the last bucket's all-reduce and update remain exposed.
+  int comm_reserve = 8;           // SMs left to NCCL while buckets are in flight (= NCCL_MAX_CTAS set at comm init)
+  bool dp_pipeline = false;       // this step updates each bucket right behind its all-reduce (train_core / cls_core)
+  int dp_opt = 0; int64_t dp_B = 0;
+  int64_t dp_covered = 0;         // parameters updated by the pipeline so far (must equal the optimizer's range at the join)
+  struct PendingAdam { int64_t b, e; };
+  std::vector<PendingAdam> pend_adam;
+  cudaEvent_t adam_gate = nullptr;
+  bool comm_busy() const { return dp_on() && buckets_in_step > 0; }
+  int64_t buckets_in_step = 0;
+
   // All-reduce G[begin, end) on the communication stream once everything enqueued so far on `stream` is done.
   int bucket_allreduce(int64_t begin, int64_t end) {
     if (!dp_on() || end <= begin) return 0;
@@ -1263,6 +1288,7 @@ struct mmae_engine {
     int r = g_nccl.AllReduce(G + begin, G + begin, (size_t)(end - begin), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, comm_stream);
     if (r != 0) return fail(MMAE_ERR_COMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
     ++buckets_issued;
+    if (end <= nP) { ++buckets_in_step; if (dp_pipeline) pend_adam.push_back({begin, end}); }
     return 0;
   }
   // bucket = the gradient range of the named variables (adjacent in the flat layout)
@@ -1272,19 +1298,37 @@ struct mmae_engine {
     if (!a || !b) return 0;
     return bucket_allreduce(a->off, b->off + align4(b->count()));
   }
-  // loss partial sums travel as the 8-float tail of G
+  // The buckets all-reduced so far may be updated once every kernel enqueued on `stream` up to here (the dgrads that
+  // still read their weights) has finished.
+  int release_adam() {
+    if (!dp_pipeline || pend_adam.empty()) return 0;
+    if (!adam_gate) CK(cudaEventCreateWithFlags(&adam_gate, cudaEventDisableTiming));
+    CK(cudaEventRecord(adam_gate, stream));
+    CK(cudaStreamWaitEvent(comm_stream, adam_gate, 0));
+    for (const PendingAdam& pa : pend_adam) {
+      RET(adam_range(dp_opt, dp_B, pa.b, pa.e, comm_stream));
+      dp_covered += pa.e - pa.b;
+    }
+    pend_adam.clear();
+    return 0;
+  }
+  // loss partial sums travel as the 8-float tail of G; unpacked on the communication stream so that the pipelined
+  // Adam kernels (RMSE gradient scale) see the global sums
   int sums_allreduce() {
     if (!dp_on()) return 0;
     RET(pack_sums());
-    return bucket_allreduce(nP, nP + 8);
+    RET(bucket_allreduce(nP, nP + 8));
+    if (dp_pipeline) { pack_sums_kernel<<<1, 32, 0, comm_stream>>>(d_sums, G + nP, 0); CKL("unpack_sums"); }
+    return 0;
   }
   // the update (and the scalars) must see fully reduced gradients
   int join_comm() {
     if (!dp_on()) return 0;
+    RET(release_adam());
     CK(cudaEventRecord(comm_done, comm_stream));
     CK(cudaStreamWaitEvent(stream, comm_done, 0));
-    comm_ev_used = 0;
-    RET(unpack_sums());
+    comm_ev_used = 0; buckets_in_step = 0;
+    if (!dp_pipeline) RET(unpack_sums());
     return 0;
   }
   int allreduce_grads() { return join_comm(); }
@@ -1304,6 +1348,34 @@ struct mmae_engine {
     finalize_scalars_kernel<<<1, 1, 0, stream>>>(a); CKL("finalize_scalars"); return 0;
   }
 
+  // Adam over G / P [b, e) of optimizer `opt` on stream `st` (alpha already prepared in StepState), then the K-major
+  // shadows of the 2-D variables in the range.
+  int adam_range(int opt, int64_t B, int64_t b, int64_t e, cudaStream_t st) {
+    AdamArgs a; a.P = P; a.G = G;
+    const int64_t base = opt == 0 ? 0 : enc_begin;
+    a.M = (opt == 0 ? M0 : M1) + (b - base); a.V = (opt == 0 ? V0 : V1) + (b - base);
+    a.begin = b; a.end = e;
+    a.segs = d_segs[opt]; a.nsegs = nsegs[opt]; a.sums = d_sums;
+    a.scale_mode = (opt == 0 && cfg.loss_func == MMAE_LOSS_RMSE) ? 1 : 0;
+    a.n_elems = (double)gbatch(B) * F;
+    a.alpha = &d_state->alpha[opt];
+    a.b1 = cfg.beta1; a.b2 = cfg.beta2; a.eps = cfg.adam_eps; a.scalars_out = d_scalars;
+    a.PT = shadow_in_adam() ? PT : nullptr;
+    adam_kernel<<<grid_for(e - b, 256), 256, 0, st>>>(a);
+    CKL("adam");
+    for (size_t i = 0; i < vars.size(); ++i) {
+      Var& v = vars[i];
+      if (v.off < b || v.off >= e) continue;
+      if (a.PT || v.cols == 0) { pt_dirty[i] = 0; continue; }
+      if (st != stream && cfg.precision == MMAE_PREC_TF32) {       // pipelined update: refresh the shadow right behind it, off the critical path
+        dim3 grid((unsigned)((v.cols + 31) / 32), (unsigned)((v.rows + 31) / 32)), block(32, 8);
+        transpose_kernel<<<grid, block, 0, st>>>(P + v.off, PT + v.off, (int)v.rows, (int)v.cols);
+        CKL("transpose");
+        pt_dirty[i] = 0;
+      } else pt_dirty[i] = 1;
+    }
+    return 0;
+  }
   int apply_update(int opt, int64_t B, bool prep_done = false) {
     if (opt == 1 && H == 0) return fail(MMAE_ERR_STATE, "no classification head");
     t_opt[opt] += 1;
@@ -1312,19 +1384,24 @@ struct mmae_engine {
       adam_prep_kernel<<<1, 1, 0, stream>>>(d_state, opt, lr, (double)cfg.beta1, (double)cfg.beta2);
       CKL("adam_prep");
     }
-    AdamArgs a; a.P = P; a.G = G;
-    a.M = opt == 0 ? M0 : M1; a.V = opt == 0 ? V0 : V1;
-    a.begin = opt == 0 ? 0 : enc_begin; a.end = opt == 0 ? enc_end : nP;
-    a.segs = d_segs[opt]; a.nsegs = nsegs[opt]; a.sums = d_sums;
-    a.scale_mode = (opt == 0 && cfg.loss_func == MMAE_LOSS_RMSE) ? 1 : 0;
-    a.n_elems = (double)gbatch(B) * F;
-    a.alpha = &d_state->alpha[opt];
-    a.b1 = cfg.beta1; a.b2 = cfg.beta2; a.eps = cfg.adam_eps; a.scalars_out = d_scalars;
-    a.PT = shadow_in_adam() ? PT : nullptr;
-    adam_kernel<<<grid_for(a.end - a.begin, 256), 256, 0, stream>>>(a);
-    CKL("adam");
-    if (a.PT) { for (size_t i = 0; i < vars.size(); ++i) if (vars[i].off >= a.begin && vars[i].off < a.end) pt_dirty[i] = 0; }
-    else mark_dirty(a.begin, a.end);
+    return adam_range(opt, B, opt == 0 ? 0 : enc_begin, opt == 0 ? enc_end : nP, stream);
+  }
+  // data-parallel step: alpha is prepared up front, every bucket is updated behind its all-reduce (release_adam)
+  int begin_dp_pipeline(int opt, int64_t B) {
+    dp_pipeline = false;
+    static const bool off = getenv("MMAE_DP_PIPELINE") && getenv("MMAE_DP_PIPELINE")[0] == '0';
+    if (!dp_on() || off) return 0;
+    const double lr = opt == 0 ? cfg.learning_rate : cfg.head_learning_rate;
+    adam_prep_kernel<<<1, 1, 0, stream>>>(d_state, opt, lr, (double)cfg.beta1, (double)cfg.beta2);
+    CKL("adam_prep");
+    dp_pipeline = true; dp_opt = opt; dp_B = B; dp_covered = 0; pend_adam.clear();
+    return 0;
+  }
+  int end_dp_pipeline(int opt) {
+    dp_pipeline = false;
+    t_opt[opt] += 1;
+    const int64_t want = opt == 0 ? enc_end : nP - enc_begin;
+    if (dp_covered != want) return fail(MMAE_ERR_STATE, "internal: the gradient buckets of the step do not cover the optimizer's variables");
     return 0;
   }
   int64_t last_B = 0;
@@ -1369,7 +1446,7 @@ bool noise_materialises(const mmae_engine* e, int64_t B) {
          !const_cast<mmae_engine*>(e)->noise_fusion_on();
 }
 int launch_sample_noise(mmae_engine* e, const float* src, uint32_t n_rows, const int64_t* idx_in, int64_t batch, int64_t first_row,
-                        float* clean_out) {
+                        float* clean_out, const int64_t* view = nullptr) {
   int r = e->ensure_acts(batch); if (r) return r;
   SampleNoiseArgs a; memset(&a, 0, sizeof(a));
   a.g.zero_bits = e->zero_bits; a.g.mod_bits = e->mod_bits; a.g.batch = batch; a.g.row0 = first_row;
@@ -1378,7 +1455,7 @@ int launch_sample_noise(mmae_engine* e, const float* src, uint32_t n_rows, const
   for (size_t i = 0; i < e->thresholds.size(); ++i) a.g.thresholds[i] = e->thresholds[i];
   for (size_t i = 0; i < e->type_masks.size(); ++i) a.g.type_masks[i] = e->type_masks[i];
   a.g.step = &e->d_state->step; a.g.seed = e->cfg.seed;
-  a.src = src; a.n_rows = n_rows; a.idx_in = idx_in; a.idx_out = n_rows ? e->d_idx : nullptr;
+  a.src = src; a.n_rows = n_rows; a.idx_in = idx_in; a.view = view; a.idx_out = n_rows ? e->d_idx : nullptr;
   a.clean_out = clean_out; a.noisy_out = e->noisy; a.col_mod = e->d_col_mod; a.mask_with = e->cfg.mask_with;
   const int64_t blocks = std::min<int64_t>((batch + SN_WARPS - 1) / SN_WARPS, (int64_t)e->num_sms * 16);
   sample_noise_kernel<<<(unsigned)blocks, SN_WARPS * 32, 0, e->stream>>>(a);
@@ -1708,17 +1785,30 @@ int mmae_apply_update(mmae_engine* e, int optimizer) {
 namespace {
 int train_core(mmae_engine* e, const float* Xd, const float* target, int64_t batch, int use_noise, float keep, bool noisy_ready = false) {
   e->fast_step = !e->dp_on(); e->step_finalized = false; e->pending_loss_partials = 0;
-  int r = do_train(e, Xd, batch, use_noise, keep, target, true, noisy_ready);
+  int r = e->begin_dp_pipeline(0, batch); if (r) return r;
+  const bool piped = e->dp_pipeline;
+  r = do_train(e, Xd, batch, use_noise, keep, target, true, noisy_ready);
   e->fast_step = false;
-  if (r) return r;
+  if (r) { e->dp_pipeline = false; return r; }
   r = e->flush_pending_loss(); if (r) return r;
   r = e->allreduce_grads(); if (r) return r;
+  if (piped) {        // alpha was prepared up front and every bucket is already updated: only the scalars and the step counter remain
+    r = e->finalize_scalars(batch, true, false, -1, true); if (r) return r;
+    return e->end_dp_pipeline(0);
+  }
   if (!e->step_finalized) { r = e->finalize_scalars(batch, true, false, 0, true); if (r) return r; }
   return e->apply_update(0, batch, true);
 }
 int cls_core(mmae_engine* e, const float* Xd, const float* Yd, int64_t batch, int use_noise, float keep, bool noisy_ready = false) {
-  int r = do_cls(e, Xd, Yd, batch, use_noise, keep, true, noisy_ready); if (r) return r;
+  int r = e->begin_dp_pipeline(1, batch); if (r) return r;
+  const bool piped = e->dp_pipeline;
+  r = do_cls(e, Xd, Yd, batch, use_noise, keep, true, noisy_ready);
+  if (r) { e->dp_pipeline = false; return r; }
   r = e->allreduce_grads(); if (r) return r;
+  if (piped) {
+    r = e->finalize_scalars(batch, false, true, -1, true); if (r) return r;
+    return e->end_dp_pipeline(1);
+  }
   r = e->finalize_scalars(batch, false, true, 1, true); if (r) return r;
   return e->apply_update(1, batch, true);
 }
@@ -1897,6 +1987,9 @@ int mmae_set_dataset(mmae_engine* e, int slot, const float* X_host, const float*
   if (ce != cudaSuccess) return e->cuda_fail(ce, "sync");
   if (e->ds_X[slot]) { cudaFree(e->ds_X[slot]); e->ds_X[slot] = nullptr; }
   if (e->ds_Y[slot]) { cudaFree(e->ds_Y[slot]); e->ds_Y[slot] = nullptr; }
+  if (e->ds_view[slot]) { cudaFree(e->ds_view[slot]); e->ds_view[slot] = nullptr; }
+  e->ds_view_rows[slot] = 0;
+  e->clear_graphs();
   ce = cudaMalloc(&e->ds_X[slot], (size_t)rows * e->F * 4);
   if (ce == cudaSuccess) ce = cudaMemcpy(e->ds_X[slot], X_host, (size_t)rows * e->F * 4, cudaMemcpyHostToDevice);
   if (ce == cudaSuccess && Y_host && label_cols > 0) {
@@ -1905,6 +1998,24 @@ int mmae_set_dataset(mmae_engine* e, int slot, const float* X_host, const float*
   }
   if (ce != cudaSuccess) return e->cuda_fail(ce, "set_dataset");
   e->ds_rows[slot] = rows; e->ds_ycols[slot] = (Y_host && label_cols > 0) ? label_cols : 0;
+  return 0;
+}
+
+int mmae_set_dataset_view(mmae_engine* e, int slot, const int64_t* rows_host, int64_t count) {
+  ENTER(e);
+  if (slot < 0 || slot > 1 || !e->ds_X[slot]) return e->fail(MMAE_ERR_STATE, "dataset slot is empty");
+  cudaError_t ce = cudaStreamSynchronize(e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "sync");
+  e->clear_graphs();
+  if (e->ds_view[slot]) { cudaFree(e->ds_view[slot]); e->ds_view[slot] = nullptr; }
+  e->ds_view_rows[slot] = 0;
+  if (!rows_host || count <= 0) return 0;                      // back to "every row of the dataset"
+  for (int64_t i = 0; i < count; ++i)
+    if (rows_host[i] < 0 || rows_host[i] >= e->ds_rows[slot]) return e->fail(MMAE_ERR_INVALID, "view row outside the dataset");
+  ce = cudaMalloc(&e->ds_view[slot], (size_t)count * 8);
+  if (ce == cudaSuccess) ce = cudaMemcpy(e->ds_view[slot], rows_host, (size_t)count * 8, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "set_dataset_view");
+  e->ds_view_rows[slot] = count;
   return 0;
 }
 
@@ -1921,25 +2032,36 @@ int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, 
   int r = e->ensure_resident(batch); if (r) return r;
   // device-side sampling (Philox row indices, gather, Philox noise) + the optimizer step: every per-step value comes
   // from StepState in device memory, so the whole sequence replays as one graph
+  const int64_t* view = e->ds_view[slot];
+  const uint32_t n_rows = (uint32_t)(view ? e->ds_view_rows[slot] : e->ds_rows[slot]);
+  if (idx_host) {
+    for (int64_t i = 0; i < batch; ++i)
+      if (idx_host[i] < 0 || idx_host[i] >= (int64_t)n_rows) return e->fail(MMAE_ERR_INVALID, "row index outside the dataset (view)");
+    if (batch > e->idx_in_cap) {
+      cudaError_t ce0 = cudaStreamSynchronize(e->stream);
+      if (ce0 != cudaSuccess) return e->cuda_fail(ce0, "sync");
+      e->clear_graphs();
+      r = e->realloc_dev(e->d_idx_in, batch); if (r) return r;
+      e->idx_in_cap = batch;
+    }
+  }
   auto body = [&]() -> int {
     cudaError_t ce;
     const int wpb = 8;
     bool noisy_ready = false;
     if (idx_host) {
-      ce = cudaMemcpyAsync(e->d_idx, idx_host, (size_t)batch * 8, cudaMemcpyHostToDevice, e->stream);
+      ce = cudaMemcpyAsync(e->d_idx_in, idx_host, (size_t)batch * 8, cudaMemcpyHostToDevice, e->stream);
       if (ce != cudaSuccess) return e->cuda_fail(ce, "H2D indices");
     }
     if (gen_noise && noise_materialises(e, batch)) {
-      // one kernel: Philox row indices (or the given ones), gather of the clean batch, descriptor, noisy batch
-      int rr = launch_sample_noise(e, e->ds_X[slot], (uint32_t)e->ds_rows[slot], idx_host ? e->d_idx : nullptr, batch, e->first_row, e->gxb);
+      // one kernel: Philox row indices (or the given ones), fold view, gather of the clean batch, descriptor, noisy batch
+      int rr = launch_sample_noise(e, e->ds_X[slot], n_rows, idx_host ? e->d_idx_in : nullptr, batch, e->first_row, e->gxb, view);
       if (rr) return rr;
       noisy_ready = true;
     } else {
-      if (!idx_host) {
-        philox_indices_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, e->stream>>>(e->d_idx, batch, e->first_row,
-                                                                                    (uint32_t)e->ds_rows[slot], &e->d_state->step, e->cfg.seed);
-        ++e->launches;
-      }
+      philox_indices_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, e->stream>>>(e->d_idx, batch, e->first_row, n_rows, &e->d_state->step,
+                                                                                  e->cfg.seed, idx_host ? e->d_idx_in : nullptr, view);
+      ++e->launches;
       gather_rows_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, e->stream>>>(e->ds_X[slot], e->d_idx, e->gxb, batch, e->F);
       ++e->launches;
       if (gen_noise) { int rr = launch_noise_gen(e, batch, e->first_row); if (rr) return rr; }
@@ -1954,8 +2076,49 @@ int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, 
                           : train_core(e, e->gxb, nullptr, batch, gen_noise ? 1 : 0, keep, noisy_ready);
   };
   if (idx_host || e->sticky) return body();            // host-supplied indices: pageable copy, stay eager
-  return e->run_graphed(graph_key(e, 2 + slot * 2 + (classification ? 1 : 0), e->ds_X[slot], e->ds_Y[slot], nullptr, batch, gen_noise ? 1 : 0, keep),
+  return e->run_graphed(graph_key(e, 2 + slot * 2 + (classification ? 1 : 0), e->ds_X[slot], e->ds_Y[slot], view, batch, gen_noise ? 1 : 0, keep),
                         classification ? 1 : 0, batch, body);
+}
+
+int mmae_modality_rmse(mmae_engine* e, const float* X_host, int64_t rows, double* rmse_host) {
+  ENTER(e);
+  if (!X_host || rows <= 0 || !rmse_host) return e->fail(MMAE_ERR_INVALID, "bad arguments");
+  if (e->sticky) return e->fail(MMAE_ERR_CUDA, "engine is in a sticky CUDA error state: " + e->err);
+  const int M = e->M, F = e->F;
+  // rows travel in chunks of n; each chunk is one forward over its M masked copies (M * n rows)
+  const int64_t n = std::min<int64_t>(rows, std::max<int64_t>(1024, ((int64_t)1 << 20) / M));
+  int r = e->ensure_host(n); if (r) return r;
+  r = e->ensure_acts(n * M); if (r) return r;
+  const int nblk = e->num_sms * 2;
+  double* d_part = nullptr; double* d_sse = nullptr;
+  cudaError_t ce = cudaMalloc(&d_part, (size_t)M * nblk * 8);
+  if (ce == cudaSuccess) ce = cudaMalloc(&d_sse, (size_t)M * 8);
+  if (ce != cudaSuccess) { cudaFree(d_part); return e->cuda_fail(ce, "modality_rmse scratch"); }
+  int rc = 0;
+  for (int64_t r0 = 0; r0 < rows && rc == 0; r0 += n) {
+    const int64_t nr = std::min(n, rows - r0);
+    float* Xd = nullptr;
+    int t = stage_host(e, X_host + r0 * F, nullptr, nr, 0, &Xd, nullptr);
+    if (t < 0) { rc = t; break; }
+    modality_mask_batch_kernel<<<e->grid_for((int64_t)M * nr * F, 256), 256, 0, e->stream>>>(Xd, e->noisy, nr, F, M, e->d_col_mod);
+    ++e->launches;
+    rc = e->begin_step(nr * M, false); if (rc) break;
+    mmae_engine::FwdOpts o; o.X = e->noisy; o.target = nullptr; o.labels = nullptr; o.B = nr * M; o.noise = false; o.keep = 1.f;
+    o.train_recon = false; o.decoder = true; o.headp = false; o.recon_out = nullptr; o.need_mu = false;
+    rc = e->forward(o); if (rc) break;
+    modality_sse_kernel<<<dim3(nblk, M), 256, 0, e->stream>>>(Xd, e->out, nr, F, e->d_starts, M, d_part);
+    modality_sse_reduce_kernel<<<M, 32, 0, e->stream>>>(d_part, nblk, d_sse, e->d_starts, rows, r0 + nr >= rows ? 1 : 0, r0 == 0 ? 1 : 0);
+    e->launches += 2;
+    if (e->cfg.variational) { rc = e->advance_step(); if (rc) break; }
+    rc = release_stage(e, t);
+  }
+  if (rc == 0) {
+    ce = cudaMemcpyAsync(rmse_host, d_sse, (size_t)M * 8, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) rc = e->cuda_fail(ce, "modality_rmse");
+  } else cudaStreamSynchronize(e->stream);
+  cudaFree(d_part); cudaFree(d_sse);
+  return rc;
 }
 
 int mmae_read_scalars(mmae_engine* e, double* out, int count) {
@@ -1981,6 +2144,18 @@ int mmae_comm_init(mmae_engine* e, const void* id_128, int rank, int world_size)
   std::string err;
   if (!load_nccl(err)) return e->fail(MMAE_ERR_COMM, err);
   Id128 id; memcpy(&id, id_128, 128);
+  // NCCL's CTAs cannot share an SM with a 227 KB GEMM CTA: give the collectives a fixed, small number of SMs and size
+  // the persistent GEMM grids around them (mmae_engine::gemm).  MMAE_NCCL_CTAS overrides; an NCCL_MAX_CTAS already in
+  // the environment wins.
+  {
+    const char* ev = getenv("MMAE_NCCL_CTAS");
+    int ctas = ev ? atoi(ev) : 8;
+    if (ctas < 1) ctas = 1; if (ctas > 32) ctas = 32;
+    char buf[16]; snprintf(buf, 16, "%d", ctas);
+    setenv("NCCL_MAX_CTAS", buf, 0);
+    const char* got = getenv("NCCL_MAX_CTAS");
+    e->comm_reserve = got ? std::max(1, atoi(got)) : ctas;
+  }
   int r = g_nccl.CommInitRank(&e->comm, world_size, id, rank);
   if (r != 0) return e->fail(MMAE_ERR_COMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
   e->world = world_size; e->rank = rank;

@@ -97,7 +97,9 @@ struct SampleNoiseArgs {
   const float* src;               // dataset [n_rows, F] (gather) or the batch itself [batch, F]
   uint32_t n_rows;                // > 0: sample row indices into src;  0: src is the batch
   const int64_t* idx_in;          // optional host-supplied indices (n_rows > 0)
-  int64_t* idx_out;               // optional: the sampled indices
+  const int64_t* view;            // optional: row list of the current training view (a cross-validation fold): sampled
+                                  // index j means dataset row view[j];  n_rows is then the length of the view
+  int64_t* idx_out;               // optional: the dataset rows that were gathered
   float* clean_out;               // gathered clean batch (null when src is the batch)
   float* noisy_out;               // noisy batch
   const uint8_t* col_mod; float mask_with;
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(SN_WARPS * 32) sample_noise_kernel(const Sampl
     int64_t srow = row;
     if (a.n_rows) {
       srow = a.idx_in ? a.idx_in[row] : (int64_t)mulhi_u32(philox_word((uint64_t)grow, kStreamBatch, step, a.g.seed), a.n_rows);
+      if (a.view) srow = __ldg(a.view + srow);
       if (lane == 0 && a.idx_out) a.idx_out[row] = srow;
     }
     __syncwarp();
@@ -236,11 +239,13 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int64_t*
   }
 }
 
+// idx[i] = dataset row of batch row i: Philox draw in [0, n_rows) (or the given index), mapped through the optional view
 __global__ void philox_indices_kernel(int64_t* idx, int64_t batch, int64_t first, uint32_t n_rows,
-                                      const uint32_t* step, uint64_t seed) {
+                                      const uint32_t* step, uint64_t seed, const int64_t* given, const int64_t* view) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch) return;
-  idx[i] = (int64_t)mulhi_u32(philox_word((uint64_t)(i + first), kStreamBatch, __ldg(step), seed), n_rows);
+  int64_t j = given ? given[i] : (int64_t)mulhi_u32(philox_word((uint64_t)(i + first), kStreamBatch, __ldg(step), seed), n_rows);
+  idx[i] = view ? __ldg(view + j) : j;
 }
 
 // ------------------------------------------------------------------ column sums (bias gradients)
@@ -513,6 +518,55 @@ __global__ void fill_select_kernel(const float* __restrict__ X, const float* __r
     int64_t r = i / num_feats; int c = (int)(i - r * num_feats);
     out[i] = ((__ldg(miss + r) >> __ldg(col_mod + c)) & 1u) ? __ldg(recon + i) : __ldg(X + i);
   }
+}
+
+// ------------------------------------------------------------------ per-modality reconstruction error (:1189-1216)
+// get_reconstruction_loss_per_modality as ONE batched pass: the M masked copies of the rows are stacked into one
+// [M * n, F] batch (copy m has modality m set to the literal -1.0, :1203), one forward reconstructs all of them, and
+// the squared error of every copy's own block is reduced in-kernel.
+__global__ void modality_mask_batch_kernel(const float* __restrict__ X, float* __restrict__ out, int64_t n, int num_feats,
+                                           int num_mod, const uint8_t* __restrict__ col_mod) {
+  const int64_t total = (int64_t)num_mod * n * num_feats;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % num_feats);
+    const int64_t rr = i / num_feats;
+    const int m = (int)(rr / n);
+    const int64_t r = rr - (int64_t)m * n;
+    out[i] = (__ldg(col_mod + c) == m) ? -1.0f : __ldg(X + r * num_feats + c);
+  }
+}
+// partial[m * gridDim.x + blockIdx.x] = sum over this block's rows of copy m, columns of block m, of (X - recon)^2
+__global__ void modality_sse_kernel(const float* __restrict__ X, const float* __restrict__ recon, int64_t n, int num_feats,
+                                    const int32_t* __restrict__ starts, int num_mod, double* __restrict__ partial) {
+  __shared__ double red[8];
+  const int m = blockIdx.y;
+  const int s = starts[m], e = starts[m + 1], w = e - s;
+  double acc = 0.0;
+  const int64_t total = n * (int64_t)w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / w; const int c = s + (int)(i - r * w);
+    const float d = __ldg(X + r * num_feats + c) - __ldg(recon + ((int64_t)m * n + r) * num_feats + c);
+    acc += (double)d * (double)d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    partial[(int64_t)m * gridDim.x + blockIdx.x] = t;
+  }
+}
+// sse[m] += sum of the block partials (fixed order); with finish != 0: rmse[m] = sqrt(sse[m] / (rows * width_m))
+__global__ void modality_sse_reduce_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ sse,
+                                           const int32_t* __restrict__ starts, int64_t rows_total, int finish, int reset) {
+  const int m = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  double t = reset ? 0.0 : sse[m];
+  for (int i = 0; i < nblocks; ++i) t += partial[(int64_t)m * nblocks + i];
+  const int w = starts[m + 1] - starts[m];
+  sse[m] = finish ? (w > 0 && rows_total > 0 ? sqrt(t / ((double)rows_total * w)) : nan("")) : t;
 }
 
 // ------------------------------------------------------------------ small glue kernels

@@ -281,9 +281,21 @@ class DataLoader:
         val_X, val_Y = self._split(val_df, None)
         return train_X, train_Y, val_X, val_Y
 
+    def cross_val_base(self):
+        """(X, Y) of every row that takes part in cross validation (fold != -1), in DataFrame order: the matrix a
+        device-resident pipeline uploads ONCE; each fold is then the row list `train_index` into it."""
+        if getattr(self, '_cv_base', None) is None:
+            cv = self.df['logistics_cv_fold']
+            self._cv_base = self._split(self.df[cv != -1], None)
+            self._cv_fold_of_row = cv[cv != -1].to_numpy()
+        return self._cv_base
+
     def set_to_cross_validation_fold(self, fold):
         self.fold = fold
         self.train_X, self.train_Y, self.val_X, self.val_Y = self.get_cross_val_data_for_fold(fold)
+        self.cross_val_base()
+        # rows of the base matrix this fold trains on, in the order of train_X (train_X == base_X[train_index])
+        self.train_index = np.nonzero(self._cv_fold_of_row != fold)[0].astype(np.int64)
         if self.separate_noisy_data:
             self.set_noisy_clean_data_for_fold(fold)
 

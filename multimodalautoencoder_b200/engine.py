@@ -427,6 +427,15 @@ class Engine:
             yp = Y.ctypes.data_as(C.c_void_p)
         self._ck(self.lib.mmae_set_dataset(self._h, slot, X.ctypes.data_as(C.c_void_p), yp, X.shape[0], yc))
 
+    def set_dataset_view(self, slot, rows=None):
+        """Training view of the resident dataset in `slot`: the dataset rows the current cross-validation fold trains on
+        (None: all rows).  Sampled / given indices address the view."""
+        if rows is None:
+            self._ck(self.lib.mmae_set_dataset_view(self._h, slot, None, 0))
+            return
+        r = np.ascontiguousarray(rows, np.int64)
+        self._ck(self.lib.mmae_set_dataset_view(self._h, slot, r.ctypes.data_as(C.c_void_p), r.size))
+
     def train_step_resident(self, slot, batch, idx=None, gen_noise=True, keep=1.0, classification=False):
         ip = None
         if idx is not None:
@@ -434,6 +443,14 @@ class Engine:
             ip = idx.ctypes.data_as(C.c_void_p)
         self._ck(self.lib.mmae_train_step_resident(self._h, slot, ip, int(batch), int(bool(gen_noise)), float(keep),
                                                    int(bool(classification))))
+
+    def modality_rmse(self, X_host):
+        """get_reconstruction_loss_per_modality (:1189-1216) in one batched device pass: list of M RMSE values."""
+        X = np.ascontiguousarray(X_host, np.float32)
+        M = len(self.cfg.modality_starts) - 1
+        out = (C.c_double * M)()
+        self._ck(self.lib.mmae_modality_rmse(self._h, X.ctypes.data_as(C.c_void_p), X.shape[0], out))
+        return [float(out[i]) for i in range(M)]
 
     def scalars(self):
         a = (C.c_double * capi.NUM_SCALARS)()

@@ -215,6 +215,7 @@ class MultimodalAutoencoder:
                       'predictions', 'accuracy'):
                 setattr(self, n, _Handle(n))
         self._resident = {}
+        self._resident_view = {}
         self._step_count = 0
 
     def initialize_network_weights(self):
@@ -355,10 +356,24 @@ class MultimodalAutoencoder:
         eng = self.engine
         dl = self.classification_data_loader if classification else self.data_loader
         slot = 1 if classification else 0
-        key = (id(dl.train_X), getattr(dl, 'fold', None), len(dl.train_X))
-        if self._resident.get(slot) != key:
-            eng.set_dataset(slot, dl.train_X, dl.train_Y if classification else None)
-            self._resident[slot] = key
+        if getattr(dl, 'cross_validation', False) and getattr(dl, 'train_index', None) is not None:
+            # cross validation: the base matrix goes to the device once, a fold is a row list (set_dataset_view)
+            bX, bY = dl.cross_val_base()
+            key = ('cv', id(bX), len(bX))
+            if self._resident.get(slot) != key:
+                eng.set_dataset(slot, bX, bY if classification else None)
+                self._resident[slot] = key
+                self._resident_view[slot] = None
+            vkey = (dl.fold, len(dl.train_index))
+            if self._resident_view.get(slot) != vkey:
+                eng.set_dataset_view(slot, dl.train_index)
+                self._resident_view[slot] = vkey
+        else:
+            key = (id(dl.train_X), getattr(dl, 'fold', None), len(dl.train_X))
+            if self._resident.get(slot) != key:
+                eng.set_dataset(slot, dl.train_X, dl.train_Y if classification else None)
+                self._resident[slot] = key
+                self._resident_view[slot] = None
         B = self.classification_batch_size if classification else self.batch_size
         keep = self.classification_dropout_prob if classification else self.dropout_prob
         for step in range(num_steps):
@@ -636,33 +651,16 @@ class MultimodalAutoencoder:
 
     def get_reconstruction_loss_per_modality(self, X):
         """Per modality: mask it with literal -1.0 for every row, reconstruct, RMSE on that block (:1189-1216)."""
-        X = np.asarray(X, np.float64)
         dl = self.data_loader
-        rms = [np.nan] * len(dl.modality_names)
-        if float(self.mask_with) == -1.0 and not self.variational and len(X) > 0:
-            # X travels to the device once; each modality is masked there through the noise descriptor (modality bit set
-            # for every row, no zero cells) and the block RMSE is reduced on the device: no per-modality host copy,
-            # upload and download of the whole matrix.  (The reference masks with the literal -1.0, :1203.)
-            eng = self.engine
-            torch = eng._torch
-            Xd = eng._dev(np.ascontiguousarray(X, np.float32))
-            zb = np.zeros((len(X), (dl.num_feats + 31) // 32), np.uint32)
-            for i, name in enumerate(dl.modality_names):
-                s, e = dl.modality_start_indices[i], dl.modality_start_indices[i + 1]
-                eng.set_noise(zb, np.full(len(X), 1 << i, np.uint32))
-                rec = eng.forward(Xd, noise=True, recon=True)['recon']
-                rms[i] = float(torch.sqrt(torch.mean((rec[:, s:e].double() - Xd[:, s:e].double()) ** 2)).item()) if e > s else np.nan
-                if self.verbose:
-                    print("RMS for modality", name, "is", rms[i])
-            return rms
-        for i, name in enumerate(dl.modality_names):
-            s, e = dl.modality_start_indices[i], dl.modality_start_indices[i + 1]
-            noisy = X.copy()
-            noisy[:, s:e] = -1.0
-            recon, _ = self.predict(noisy)
-            rms[i] = get_rmse(X[:, s:e], recon[:, s:e])
-            if self.verbose:
-                print("RMS for modality", name, "is", rms[i])
+        if len(X) == 0:
+            return [np.nan] * len(dl.modality_names)
+        # One batched device pass (mmae_modality_rmse): the M masked copies of the rows form one batch, one forward
+        # reconstructs them all, the squared errors of each copy's own block are reduced on the device.  The mask value
+        # is the literal -1.0, as in the reference (:1203), whatever mask_with is.
+        rms = self.engine.modality_rmse(X)
+        if self.verbose:
+            for name, v in zip(dl.modality_names, rms):
+                print("RMS for modality", name, "is", v)
         return rms
 
     # ------------------------------------------------------------------ plots (optional dependency)

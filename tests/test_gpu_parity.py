@@ -438,3 +438,44 @@ def test_loss_curve_over_1k_steps(prec):
     cv = O.forward(ocfg, P, Xv, Xv)
     assert abs(e.scalars()['recon_loss'] - cv['recon_loss']) <= 1e-3 * cv['recon_loss']
     e.close()
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'tf32'])
+def test_resident_dataset_view_is_an_index_list(prec):
+    """Cross-validation folds as views: base matrix on the device once, a fold = row list.  Sampling through the view is
+    bit-identical to uploading the fold's rows as a dataset of their own (Philox indices and explicit ones)."""
+    ocfg, ecfg = make_cfgs(precision=prec)
+    rng, X = _data(ocfg, 1000, 10)
+    P = O.init_params(ocfg, rng)
+    view = np.sort(rng.choice(1000, size=700, replace=False)).astype(np.int64)
+    a, b = _engine(ecfg, P), _engine(ecfg, P)
+    a.set_dataset(0, X); a.set_dataset_view(0, view)
+    b.set_dataset(0, X[view])
+    for step, idx in ((5, None), (6, rng.integers(0, 700, 128))):
+        a.set_rng_step(step); b.set_rng_step(step)
+        a.train_step_resident(0, 128, idx=idx, gen_noise=True)
+        b.train_step_resident(0, 128, idx=idx, gen_noise=True)
+    for k in P:
+        assert np.array_equal(a.get_variable(k), b.get_variable(k)), k
+    with pytest.raises(ValueError):
+        a.train_step_resident(0, 4, idx=np.array([0, 1, 2, 700]), gen_noise=True)       # outside the view
+    a.set_dataset_view(0, None)
+    a.set_rng_step(9); b.set_dataset(0, X); b.set_rng_step(9)
+    a.train_step_resident(0, 64, gen_noise=True); b.train_step_resident(0, 64, gen_noise=True)
+    for k in P:
+        assert np.array_equal(a.get_variable(k), b.get_variable(k)), k
+    a.close(); b.close()
+
+
+def test_modality_rmse_batched_pass():
+    """get_reconstruction_loss_per_modality as one batched device pass (M masked copies stacked, in-kernel reduction)."""
+    ocfg, ecfg = make_cfgs(precision='fp32', tie=False, loss='mean_squared')
+    rng, X = _data(ocfg, 777, 3)
+    P = O.init_params(ocfg, rng)
+    e = _engine(ecfg, P)
+    k0 = e.kernel_launches
+    got = e.modality_rmse(X.astype(np.float32))
+    assert e.kernel_launches - k0 <= 12, 'one masked-batch pass: mask, forward, reduction'
+    want = O.reconstruction_loss_per_modality(ocfg, P, X.astype(np.float32).astype(np.float64))
+    assert np.allclose(got, want, rtol=1e-5)
+    e.close()

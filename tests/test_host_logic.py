@@ -58,6 +58,9 @@ def test_data_loader_contract():
     for f in range(5):
         cv.set_to_cross_validation_fold(f)
         sizes.append(len(cv.val_X))
+        # a fold is a row list into the base matrix that a device-resident pipeline uploads once
+        bX, _ = cv.cross_val_base()
+        assert np.array_equal(bX[cv.train_index], cv.train_X) and len(bX) == len(cv.train_X) + len(cv.val_X)
         assert len(cv.train_X) + len(cv.val_X) == int((df['dataset'] != 'Test').sum())
     assert sum(sizes) == int((df['dataset'] != 'Test').sum())
 
