@@ -262,7 +262,11 @@ struct mmae_engine {
     CK(cudaGetDevice(&device));
     CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+    {      // collectives on the highest-priority stream: their CTAs are placed as soon as a persistent GEMM grid retires
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&comm_stream, cudaStreamNonBlocking, hi));
+    }
     CK(cudaEventCreateWithFlags(&comm_done, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&xin_free[i], cudaEventDisableTiming));
@@ -559,7 +563,10 @@ struct mmae_engine {
       const int max_s = allow_splitk && ep.mode == EPI_PLAIN ? 64 : 1;
       // While gradient buckets are being all-reduced, NCCL's CTAs hold SMs of their own (they cannot share one with a
       // 227 KB GEMM CTA); a persistent grid sized for all 148 SMs would then need a second wave for its last CTAs.
-      const int sms_eff = comm_busy() ? std::max(2, (num_sms - comm_reserve) & ~1) : num_sms;
+      // The reservation lasts for the launches that can overlap the bucket just issued (reserve_credits), not for the
+      // whole backward pass: the collectives are busy for about a third of it.
+      int sms_eff = num_sms;
+      if (comm_busy() && reserve_credits > 0) { sms_eff = std::max(2, (num_sms - comm_reserve) & ~1); --reserve_credits; }
       TcPlan pl = two_sm ? tc2_plan(g, sms_eff, max_s) : tc_plan(g, sms_eff, max_s);
       if (pl.splits > 1) RET(ensure_splitk((int64_t)pl.splits * m * n));
       int pr = prof_begin(2.0 * (double)m * (double)n * (double)k);
@@ -1199,6 +1206,8 @@ struct mmae_engine {
         snprintf(wn, 32, "decode_weights%d", i);
         RET(gemm(true, false, din, dout, B, u_in, din, d, ldd, gvar(wn), dout, noise_view(false), ew, nullptr, true));
       }
+      // this decoder layer's gradients are final: their all-reduce starts behind the wgrad, beside the dgrad below
+      if (cfg.tie_weights) RET(bucket_vars(bn, bn)); else RET(bucket_vars(wn, bn));
       Epilogue ed = epi(j > 0 ? EPI_DGRAD : EPI_PLAIN);
       if (j > 0) { ed.saved = da[j - 1]; ed.lds = din; ed.act = cfg.activation; if (keep < 1.f) set_dropout(ed, keep, 32u + (uint32_t)(j - 1), din); }
       ed.colsum_partials = colpart;
@@ -1206,8 +1215,7 @@ struct mmae_engine {
       RET(gemm(false, !cfg.tie_weights, B, din, dout, d, ldd, pvar(wn), cfg.tie_weights ? din : dout, nxt, din,
                noise_view(false), ed, nullptr, false));
       d_fused = last_gemm_tc;
-      if (cfg.tie_weights) RET(bucket_vars(bn, bn)); else RET(bucket_vars(wn, bn));   // this decoder layer's gradients are final
-      RET(release_adam());
+      RET(release_adam());          // the dgrad that reads D_j is enqueued: the bucket's update may follow its all-reduce
       d = nxt; ldd = din; nxt = (nxt == dA) ? dB : dA;
     }
     if (cfg.variational) {
@@ -1266,7 +1274,7 @@ struct mmae_engine {
 
   // ---- data-parallel pipeline: per-bucket all-reduce, then that bucket's Adam + shadow refresh, all on comm_stream
   // while backward keeps running on `stream`.  Only the last bucket's all-reduce and update remain exposed.
-  int comm_reserve = 8;           // SMs left to NCCL while buckets are in flight (= NCCL_MAX_CTAS set at comm init)
+  int comm_reserve = 32;          // SMs left to NCCL while buckets are in flight (= NCCL_MAX_CTAS set at comm init)
   bool dp_pipeline = false;       // this step updates each bucket right behind its all-reduce (train_core / cls_core)
   int dp_opt = 0; int64_t dp_B = 0;
   int64_t dp_covered = 0;         // parameters updated by the pipeline so far (must equal the optimizer's range at the join)
@@ -1275,6 +1283,7 @@ struct mmae_engine {
   cudaEvent_t adam_gate = nullptr;
   bool comm_busy() const { return dp_on() && buckets_in_step > 0; }
   int64_t buckets_in_step = 0;
+  int reserve_credits = 0;        // GEMM launches that still run beside the bucket issued last
 
   // All-reduce G[begin, end) on the communication stream once everything enqueued so far on `stream` is done.
   int bucket_allreduce(int64_t begin, int64_t end) {
@@ -1285,10 +1294,15 @@ struct mmae_engine {
     cudaEvent_t ev = comm_events[comm_ev_used++];
     CK(cudaEventRecord(ev, stream));
     CK(cudaStreamWaitEvent(comm_stream, ev, 0));
-    int r = g_nccl.AllReduce(G + begin, G + begin, (size_t)(end - begin), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, comm_stream);
+    static const bool skip_ar = getenv("MMAE_DP_SKIP_AR") != nullptr;      // measurement only: the step without its collectives
+    int r = skip_ar ? 0 : g_nccl.AllReduce(G + begin, G + begin, (size_t)(end - begin), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, comm_stream);
     if (r != 0) return fail(MMAE_ERR_COMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
     ++buckets_issued;
-    if (end <= nP) { ++buckets_in_step; if (dp_pipeline) pend_adam.push_back({begin, end}); }
+    if (end <= nP) {
+      ++buckets_in_step;
+      reserve_credits = (end - begin) > ((int64_t)4 << 20) ? 2 : 1;        // a > 16 MB bucket outlasts one GEMM
+      if (dp_pipeline) pend_adam.push_back({begin, end});
+    }
     return 0;
   }
   // bucket = the gradient range of the named variables (adjacent in the flat layout)
@@ -1389,8 +1403,11 @@ struct mmae_engine {
   // data-parallel step: alpha is prepared up front, every bucket is updated behind its all-reduce (release_adam)
   int begin_dp_pipeline(int opt, int64_t B) {
     dp_pipeline = false;
-    static const bool off = getenv("MMAE_DP_PIPELINE") && getenv("MMAE_DP_PIPELINE")[0] == '0';
-    if (!dp_on() || off) return 0;
+    // Measured on 8 x B200 (wide workload, 8192 rows per rank): 2.06 ms per step with the update after the join against
+    // 2.10 ms with per-bucket updates on the communication stream -- the Adam and transpose kernels queue between the
+    // all-reduces and delay the buckets behind them by more than they take off the tail.  Hence opt-in.
+    static const bool on = getenv("MMAE_DP_PIPELINE") && getenv("MMAE_DP_PIPELINE")[0] == '1';
+    if (!dp_on() || !on) return 0;
     const double lr = opt == 0 ? cfg.learning_rate : cfg.head_learning_rate;
     adam_prep_kernel<<<1, 1, 0, stream>>>(d_state, opt, lr, (double)cfg.beta1, (double)cfg.beta2);
     CKL("adam_prep");
@@ -2149,7 +2166,7 @@ int mmae_comm_init(mmae_engine* e, const void* id_128, int rank, int world_size)
   // the environment wins.
   {
     const char* ev = getenv("MMAE_NCCL_CTAS");
-    int ctas = ev ? atoi(ev) : 8;
+    int ctas = ev ? atoi(ev) : 32;      // measured: 33.5 MB bucket 160 us at 32 CTAs, 185 us at 16, 282 us at 8 (profiles/r02_allreduce_8gpu.txt)
     if (ctas < 1) ctas = 1; if (ctas > 32) ctas = 32;
     char buf[16]; snprintf(buf, 16, "%d", ctas);
     setenv("NCCL_MAX_CTAS", buf, 0);
