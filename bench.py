@@ -7,9 +7,14 @@ untied, softsign, sigmoid-CE, global batch 65536, data-parallel over the ranks (
 65536/N rows per rank, one sum-allreduce of the flat gradient per step).  One "step" = Philox
 block-mask noise + forward + backward + fused Adam over one synthetic batch.
 
-  value    device-resident inputs, CUDA-event timed, whole-job samples/s (max over ranks)
+  value    device-resident DATASET, CUDA-event timed, whole-job samples/s (max over ranks).  One step = what
+           MultimodalAutoencoder.train does per iteration (multimodal_autoencoder.py:565-590): sample the batch rows
+           (data_funcs.py:167), block-mask noise (:668-702), forward, backward, Adam -- all on the device
+           (mmae_train_step_resident)
   e2e      the same step fed from pinned HOST memory through the C ABI (mmae_train_step_host): every
            step's H2D copy and the D2H read of the loss are inside the timed region
+  api      MultimodalAutoencoder.train(rng_mode='philox') timed through the drop-in Python class
+  others   (default invocation, 1 GPU) short legs of the other BASELINE.json configs: small / cls / infer
   roofline tcgen05 GEMM family: algorithmic FLOPs / device time of those launches, measured live with
            CUDA events on the engine's stream during the timed region, against MEASURED_PEAKS.json
   cpu_baseline / --impl reference: the CPU port of the reference's step (oracle/cpu_port.py; the
@@ -150,22 +155,36 @@ def cpu_port_run(name, steps, warmup, sample_rows):
 METRIC = {'wide': 'MMAE train samples/sec (fwd+bwd+Adam)', 'small': 'MMAE train samples/sec (fwd+bwd+Adam)',
           'cls': 'MMAE train samples/sec (fwd+bwd+Adam), reconstruction step + classification-head step',
           'infer': 'MMAE fill-in inference samples/sec (reconstruction forward + missing-block fill)'}
-CPU_ROWS = {'wide': 2048, 'small': 16384, 'cls': 4096, 'infer': 65536}
+CPU_ROWS = {'wide': 2048, 'small': 16384, 'cls': 4096, 'infer': 65536}      # cpu_baseline leg inside the GPU arm (10-30 s)
+CPU_BUDGET_S = 200.0          # --impl reference: the whole --steps K --warmup W run stays within a few minutes
 
 
 def run_reference(args):
+    """The reference's CPU path for the same workload, on all host cores (rank 0 only).  TensorFlow cannot run in this
+    image, so this is the CPU port (oracle/cpu_port.py: the same op sequence on torch's multithreaded fp32 CPU kernels,
+    preceded by the reference's own per-row NumPy noise loop).  Rows per step: the workload's full batch when K + W such
+    steps fit CPU_BUDGET_S (measured with a calibration step), otherwise the largest power-of-two sample that does."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    name = args.workload
+    name = args.workload if args.workload != 'grid' else 'small'
     w, _, _ = workload_cfg(name)
-    r = cpu_port_run(name, args.steps, max(args.warmup, 1), CPU_ROWS[name])
+    full = args.rows or (w['B'] if name != 'infer' else 1_000_000)
+    cal_rows = min(full, 1024)
+    cal = cpu_port_run(name, 1, 1, cal_rows)
+    per_row = cal['seconds'] / cal_rows
+    rows = full
+    while rows > 256 and per_row * rows * (args.steps + max(args.warmup, 1)) > CPU_BUDGET_S:
+        rows //= 2
+    r = cpu_port_run(name, args.steps, max(args.warmup, 1), rows)
     line = {
         'impl': 'reference', 'metric': METRIC[name], 'value': r['value'], 'unit': 'samples/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * r['seconds'] / args.steps,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': name, 'global_batch': w['B'], 'features': w['F'], 'encoder': w['layers'],
-                   'note': 'CPU port of the reference step (TensorFlow-1.x reference cannot run here); bounded sample'},
+        'config': {'workload': name, 'global_batch': w['B'], 'features': w['F'], 'modality_blocks': len(w['blocks']),
+                   'encoder': w['layers'], 'head': w.get('head'), 'loss': w['loss'], 'activation': w['act'],
+                   'rows_per_step': rows, 'same_rows_as_gpu_arm': rows == w['B'],
+                   'note': 'CPU port of the reference step on all host cores (the TensorFlow-1.x reference cannot run here)'},
         'cpu_baseline': {'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
                          'noise_loop_share': r['noise_share']},
         'e2e': {'value': r['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -195,35 +214,29 @@ def measure_tf32_peak(torch):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='wide', choices=sorted(WORKLOADS))
-    ap.add_argument('--precision', default='tf32', choices=['tf32', 'fp32'])
-    ap.add_argument('--rows', type=int, default=0, help='override the rows per step (infer / small)')
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-e2e', action='store_true')
-    args = ap.parse_args()
-    if args.impl == 'reference':
-        return run_reference(args)
+def make_engine(name, B, precision, rng_seed=0):
+    import numpy as np
+    from multimodalautoencoder_b200 import Engine, EngineConfig
+    w, starts, names = workload_cfg(name)
+    cfg = EngineConfig(num_feats=w['F'], layer_sizes=list(w['layers']), modality_starts=starts, modality_names=names,
+                       tie_weights=w['tie'], variational=False, activation=w['act'], loss_func=w['loss'],
+                       learning_rate=1e-3, weight_penalty=0.0, seed=0, precision=precision, max_batch=B,
+                       cls_layer_sizes=w.get('head'), num_labels=w.get('labels', 3))
+    eng = Engine(cfg)
+    rng = np.random.default_rng(rng_seed)       # random-init weights of the named architecture ('normal' init, :44)
+    for vname, shp in eng.variables():
+        if len(shp) == 1:
+            eng.set_variable(vname, np.full(shp, 0.1, np.float32))
+        else:
+            eng.set_variable(vname, (np.clip(rng.standard_normal(shp), -2, 2) / np.sqrt(shp[0])).astype(np.float32))
+    return eng
 
+
+def run_leg(name, args, rank, world, local, dist, steps, warmup, want_e2e, clocks=True):
+    """One workload on this rank's GPU.  Returns the dict of measurements (rank 0 assembles the JSON line)."""
     import numpy as np
     import torch
-    from multimodalautoencoder_b200 import Engine, EngineConfig
-
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-
-    name = args.workload
+    from multimodalautoencoder_b200 import Engine
     w, starts, names = workload_cfg(name)
     train = name != 'infer'
     Bg = args.rows or w['B']
@@ -231,18 +244,7 @@ def main():
     B = Bg // world
     F = w['F']
     head = w.get('head')
-    cfg = EngineConfig(num_feats=F, layer_sizes=list(w['layers']), modality_starts=starts, modality_names=names,
-                       tie_weights=w['tie'], variational=False, activation=w['act'], loss_func=w['loss'],
-                       learning_rate=1e-3, weight_penalty=0.0, seed=0, precision=args.precision, max_batch=B,
-                       cls_layer_sizes=head, num_labels=w.get('labels', 3))
-    eng = Engine(cfg)
-    # random-init weights of the named architecture ('normal' init, multimodal_autoencoder.py:44)
-    rng = np.random.default_rng(0)
-    for vname, shp in eng.variables():
-        if len(shp) == 1:
-            eng.set_variable(vname, np.full(shp, 0.1, np.float32))
-        else:
-            eng.set_variable(vname, (np.clip(rng.standard_normal(shp), -2, 2) / np.sqrt(shp[0])).astype(np.float32))
+    eng = make_engine(name, B, args.precision)
     dp = world > 1 and train          # inference shards rows with no collective
     if dp:
         idt = torch.zeros(128, dtype=torch.uint8, device='cuda')
@@ -251,12 +253,14 @@ def main():
         dist.broadcast(idt, 0)
         eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
         eng.set_shard(Bg, rank * B)
-    # synthetic SNAPSHOT-shaped data: U[0,1) features, this rank's rows of the global batch
+    # synthetic SNAPSHOT-shaped data: U[0,1) features.  Training: a device-resident dataset of 2 x B rows per
+    # rank (each rank holds its own shard and samples it locally); inference: this rank's rows of the matrix to fill.
     gen = torch.Generator(device='cuda').manual_seed(1234 + rank)
-    X = torch.rand((B, F), device='cuda', generator=gen)
+    n_data = max(2 * B, int(300e6 / (4 * F))) if train else B      # dataset > 2 x L2 (126 MB): sampled rows come from HBM
+    X = torch.rand((n_data, F), device='cuda', generator=gen)
     Y = None
     if head:
-        Y = (torch.rand((B, w['labels']), device='cuda', generator=gen) < 0.5).float()
+        Y = (torch.rand((n_data, w['labels']), device='cuda', generator=gen) < 0.5).float()
     if not train:        # each modality of each row independently missing (-1.0) with p = 0.2
         drop = torch.rand((B, len(w['blocks'])), device='cuda', generator=gen) < 0.2
         for m in range(len(w['blocks'])):
@@ -264,15 +268,19 @@ def main():
                                                         X[:, starts[m]:starts[m + 1]])
         del drop
     filled = torch.empty((B, F), device='cuda') if not train else None
+    if train:
+        eng.set_dataset_device(0, X, Y)
+        if head:
+            eng.set_dataset_device(1, X, Y)
 
     def step(i):
         eng.set_rng_step(i)
         if name == 'infer':
             eng.forward_into(X, filled=filled)
         else:
-            eng.train_step(X, noise='gen', keep=1.0)          # Philox descriptor drawn inside the step (global rows: set_shard)
+            eng.train_step_resident(0, B, gen_noise=True)
             if name == 'cls':
-                eng.cls_train_step(X, Y, noise='gen', keep=1.0)
+                eng.train_step_resident(1, B, gen_noise=True, classification=True)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -280,10 +288,10 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     sync_all()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if (rank == 0 and clocks) else None
     if sampler:
         sampler.start()
     # The wide workload is timed with per-launch CUDA events on (profiling) inside the timed region.  The small-batch
@@ -295,8 +303,8 @@ def main():
     l0, c0, g0 = eng.kernel_launches, eng.chain_launches, eng.graph_replays
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
+    for i in range(steps):
+        step(warmup + i)
     ev1.record()
     sync_all()
     ms = ev0.elapsed_time(ev1)
@@ -305,26 +313,26 @@ def main():
     replays = eng.graph_replays - g0
     if not live_profile:
         eng.set_profiling(True)
-        for i in range(args.steps):
-            step(args.warmup + args.steps + i)
+        for i in range(steps):
+            step(warmup + steps + i)
         sync_all()
     prof = eng.read_profile()
     eng.set_profiling(False)
     sc = eng.scalars()
-    clocks = sampler.stop() if sampler else None
+    clk = sampler.stop() if sampler else None
     if dist is not None:
         t = torch.tensor([ms], device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = Bg * args.steps / (ms / 1e3)
+    value = Bg * steps / (ms / 1e3)
 
     # ---- end to end: host-fed steps through the C ABI (pinned memory, H2D + result D2H inside the timing)
     e2e = None
-    if not args.no_e2e:
+    if want_e2e:
         Be = B if train else min(B, 1_000_000)       # inference: a bounded 1 M-row slice per call (host RAM)
         hx = [torch.rand((Be, F)).pin_memory() for _ in range(2)]
         hy = (torch.rand((Be, w['labels'])) < 0.5).float().pin_memory() if head else None
-        hs = torch.zeros((args.steps + args.warmup + 1, 8), dtype=torch.float64).pin_memory()
+        hs = torch.zeros((steps + warmup + 1, 8), dtype=torch.float64).pin_memory()
         hout = torch.empty((Be, F)).pin_memory() if not train else None
 
         def estep(i):
@@ -337,13 +345,13 @@ def main():
             else:
                 eng.forward_host(hx[i % 2].numpy(), filled=True, out={'filled': hout.numpy()})
 
-        for i in range(min(args.warmup, 3)):
+        for i in range(min(warmup, 3)):
             estep(i)
         sync_all()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         t0.record()
-        for i in range(args.steps):
+        for i in range(steps):
             estep(i)
         t1.record()
         eng.synchronize()
@@ -355,22 +363,25 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         rows_e = Be * world
-        e2e = {'value': rows_e * args.steps / (ems / 1e3), 'unit': 'samples/s',
+        e2e = {'value': rows_e * steps / (ems / 1e3), 'unit': 'samples/s',
                'h2d_bytes_per_step': rows_e * F * 4 + (rows_e * w['labels'] * 4 if head else 0),
-               'd2h_bytes_per_step': 64 * world if train else rows_e * F * 4, 'ms_per_step': ems / args.steps,
-               'rows_per_step': rows_e}
+               'd2h_bytes_per_step': 64 * world if train else rows_e * F * 4, 'ms_per_step': ems / steps,
+               'rows_per_step': rows_e, 'api': 'mmae_train_step_host / mmae_forward_host (C ABI, pinned host buffers)'}
         if train:
-            e2e['last_loss'] = float(hs[args.steps - 1][0])
+            e2e['last_loss'] = float(hs[steps - 1][0])
+        del hx, hy, hout
+    eng.close()
+    del X, Y, filled
+    torch.cuda.empty_cache()
+    return dict(name=name, w=w, starts=starts, Bg=Bg, B=B, F=F, n_data=n_data, head=head, train=train, ms=ms, value=value, launches=launches,
+                chains=chains, replays=replays, prof=prof, sc=sc, clocks=clk, e2e=e2e, live_profile=live_profile, steps=steps,
+                warmup=warmup, world=world)
 
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
-        return
-    peaks, pk = measured_peaks()
+
+def roofline_of(m, peaks, pk, tf32_peak):
+    name, world, value, ms, prof = m['name'], m['world'], m['value'], m['ms'], m['prof']
     peak_tf = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops')))
     peak_bw = float(peaks.get('hbm_gbs'))
-    tf32_peak = measure_tf32_peak(torch)
     kern_ms = prof['gemm_ms']
     achieved_tf = prof['gemm_flops'] / (kern_ms / 1e3) / 1e12 if kern_ms > 0 else 0.0
     traffic = None
@@ -380,53 +391,208 @@ def main():
             traffic = json.load(f).get(name)
     if name == 'infer':
         # dominant kernel = the whole-network chain kernel; algorithmic bytes = read X + write filled X
-        algo = BYTES_PER_SAMPLE[name] * B * args.steps
+        algo = BYTES_PER_SAMPLE[name] * m['B'] * m['steps']
         ach = algo / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else 0.0
-        roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak_bw, 'unit': 'GB/s', 'frac': ach / peak_bw, 'traffic': traffic,
-                    'kernel': 'chain_tc_kernel (whole network, activations in TMEM)', 'peak_source': 'copy bandwidth, %s (MEASURED_PEAKS.json)' % pk,
-                    'algorithmic_bytes_per_launch': BYTES_PER_SAMPLE[name] * B,
-                    'kernel_share_of_step': kern_ms / ms if ms > 0 else None, 'kernel_launches': prof['gemm_launches'],
-                    'step_frac_of_peak': (BYTES_PER_SAMPLE[name] * value / world / 1e9) / peak_bw,
-                    'tensor_tflops': achieved_tf}
-    else:
-        roofline = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
-                    'traffic': traffic, 'kernel': 'gemm_tc_kernel + chain_tc_kernel (tcgen05 kind::tf32)',
-                    'peak_source': 'bf16 dense sustained, %s (MEASURED_PEAKS.json); kind::tf32 issues at half the bf16 rate, '
-                                   'so 0.5 is this kernel family\'s ceiling against this denominator' % pk,
-                    'tf32_peak_measured': tf32_peak, 'frac_of_tf32_peak': achieved_tf / tf32_peak if tf32_peak > 0 else None,
-                    'tf32_peak_source': 'cuBLAS tf32 8192^3 timed in this run (SURVEY 8d: kind::tf32 kernels are normalised by a measured TF32 peak)',
-                    'gemm_share_of_step': kern_ms / ms if ms > 0 else None,
-                    'kernel_times': 'CUDA events inside the timed region' if live_profile else 'CUDA events in a second pass of the same steps (the timed pass replays CUDA graphs)',
-                    'gemm_launches': prof['gemm_launches'],
-                    'step_frac_of_peak': (FLOPS_PER_SAMPLE[name] * value / world / 1e12) / peak_tf,
-                    'step_frac_of_tf32_peak': (FLOPS_PER_SAMPLE[name] * value / world / 1e12) / tf32_peak if tf32_peak > 0 else None}
-        if name in BYTES_PER_SAMPLE:      # small configs: the HBM bound beside the tensor bound (SURVEY 8d reports both)
-            roofline['hbm_bound'] = {'algorithmic_GBps': BYTES_PER_SAMPLE[name] * value / world / 1e9, 'peak': peak_bw,
-                                     'frac': BYTES_PER_SAMPLE[name] * value / world / 1e9 / peak_bw}
+        return {'bound': 'hbm', 'achieved': ach, 'peak': peak_bw, 'unit': 'GB/s', 'frac': ach / peak_bw, 'traffic': traffic,
+                'kernel': 'chain_tc_kernel (whole network, activations in TMEM)', 'peak_source': 'copy bandwidth, %s (MEASURED_PEAKS.json)' % pk,
+                'algorithmic_bytes_per_launch': BYTES_PER_SAMPLE[name] * m['B'],
+                'kernel_share_of_step': kern_ms / ms if ms > 0 else None, 'kernel_launches': prof['gemm_launches'],
+                'step_frac_of_peak': (BYTES_PER_SAMPLE[name] * value / world / 1e9) / peak_bw, 'tensor_tflops': achieved_tf}
+    r = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
+         'traffic': traffic,
+         'kernel': 'tcgen05 kind::tf32 family: gemm_tc2_kernel / gemm_tc_kernel (per-layer GEMMs), chain_tc_kernel<fwd|bwd> '
+                   '(whole network / all dgrads), wgrad_group_kernel (all weight gradients)',
+         'peak_source': 'bf16 dense sustained, %s (MEASURED_PEAKS.json); kind::tf32 issues at half the bf16 rate, '
+                        'so 0.5 is this kernel family\'s ceiling against this denominator' % pk,
+         'tf32_peak_measured': tf32_peak, 'frac_of_tf32_peak': achieved_tf / tf32_peak if tf32_peak > 0 else None,
+         'tf32_peak_source': 'cuBLAS tf32 8192^3 timed in this run (SURVEY 8d: kind::tf32 kernels are normalised by a measured TF32 peak)',
+         'gemm_share_of_step': kern_ms / ms if ms > 0 else None,
+         'kernel_times': 'CUDA events inside the timed region' if m['live_profile'] else 'CUDA events in a second pass of the same steps (the timed pass replays CUDA graphs)',
+         'gemm_launches': prof['gemm_launches'],
+         'step_frac_of_peak': (FLOPS_PER_SAMPLE[name] * value / world / 1e12) / peak_tf,
+         'step_frac_of_tf32_peak': (FLOPS_PER_SAMPLE[name] * value / world / 1e12) / tf32_peak if tf32_peak > 0 else None}
+    if name in BYTES_PER_SAMPLE:      # small configs: the HBM bound beside the tensor bound (SURVEY 8d reports both)
+        r['hbm_bound'] = {'algorithmic_GBps': BYTES_PER_SAMPLE[name] * value / world / 1e9, 'peak': peak_bw,
+                          'frac': BYTES_PER_SAMPLE[name] * value / world / 1e9 / peak_bw}
+        r['binding_roof'] = 'tensor: 60 % of the HBM roof (%.2f G samples/s) lies above the tf32 compute bound (%.2f G samples/s)' % (
+            0.6 * peak_bw / BYTES_PER_SAMPLE[name], tf32_peak * 1e3 / FLOPS_PER_SAMPLE[name]) if tf32_peak > 0 else None
+    return r
+
+
+def config_of(m):
+    w, B, F = m['w'], m['B'], m['F']
+    return {'workload': m['name'], 'global_batch': m['Bg'], 'features': F, 'modality_blocks': len(w['blocks']),
+            'encoder': w['layers'], 'head': m['head'], 'loss': w['loss'], 'activation': w['act'],
+            'parallelism': ('dp%d' % m['world']) if m['train'] else ('rows sharded over %d GPU(s), no collective' % m['world']),
+            'batch_source': ('device-resident dataset of %d rows per rank, %d rows sampled per step on the device (Philox)' % (m['n_data'], B))
+                            if m['train'] else 'device-resident matrix',
+            'l2_policy': 'inputs larger than L2: %s %.2f GB per rank (L2 = 126 MB), %s' % (
+                'dataset' if m['train'] else 'matrix', m['n_data'] * F * 4 / 1e9,
+                'rows sampled at random every step' if m['train'] else 'streamed once per pass'),
+            'noise': 'philox block-mask + 5% zero noise drawn on device every step' if m['train'] else
+                     'each modality block of each row missing (-1) with p = 0.2'}
+
+
+def api_leg(name, steps):
+    """MultimodalAutoencoder.train(rng_mode='philox') through the drop-in Python class at the workload's shape."""
+    import numpy as np
+    import torch
+    from multimodalautoencoder_b200 import MultimodalAutoencoder
+    from types import SimpleNamespace
+    w, starts, names = workload_cfg(name)
+    B, F = w['B'], w['F']
+    rng = np.random.default_rng(7)
+    n = 2 * B
+    X = rng.random((n, F), dtype=np.float32)
+    dl = SimpleNamespace(train_X=X, val_X=X[:400], test_X=X[:400], train_Y=None, val_Y=None, test_Y=None, num_feats=F,
+                         num_labels=None, modality_start_indices=list(starts), modality_names=list(names),
+                         num_modalities=len(names), fold=None, wanted_feats=None,
+                         get_unsupervised_train_batch=lambda b: X[np.random.choice(n, size=b)],
+                         get_unsupervised_val_batch=lambda b: X[np.random.choice(400, size=b)])
+    m = MultimodalAutoencoder(data_loader=dl, layer_sizes=list(w['layers']), variational=False, tie_weights=w['tie'],
+                              batch_size=B, learning_rate=1e-3, activation_func=w['act'], loss_func=w['loss'],
+                              weight_initialization='normal', verbose=False, rng_mode='philox', precision='tf32')
+    m.train(3, record_every_nth=10 ** 9, save_every_nth=10 ** 9)          # uploads the dataset, captures / warms the step
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    m.train(steps, record_every_nth=steps, save_every_nth=10 ** 9)        # one record step (loss read-back) in the timed region
+    m.engine.synchronize()
+    dt = time.perf_counter() - t0
+    out = {'value': B * steps / dt, 'unit': 'samples/s', 'ms_per_step': 1e3 * dt / steps, 'steps': steps,
+           'call': "MultimodalAutoencoder(..., rng_mode='philox').train(%d)" % steps, 'train_loss_per_sample': float(m.train_loss[-1])}
+    m.close()
+    return out
+
+
+def run_grid(args, rank, world, local, dist):
+    """BASELINE.json configs[2]: 64 MMAE settings fitted independently, round-robin over the ranks, no collective."""
+    import itertools
+    import numpy as np
+    import torch
+    from multimodalautoencoder_b200 import MultimodalAutoencoder
+    from multimodalautoencoder_b200.data_funcs import DataLoader
+    from multimodalautoencoder_b200.synthetic import make_frame
+    steps = args.grid_steps
+    df = make_frame(4000, seed=3)
+    dl = DataLoader(df=df, supervised=False, cross_validation=False, normalize_and_fill=False, suppress_output=True)
+    settings = list(itertools.product([[1000, 100], [500, 100], [300, 100], [128, 64]], [True, False], [1.0, 0.5], [0.0, 0.001],
+                                      ['softsign', 'relu']))
+    mine = settings[rank::world]
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    losses = []
+    for (arch, tie, keep, lam, act) in mine:
+        m = MultimodalAutoencoder(data_loader=dl, layer_sizes=arch, variational=False, tie_weights=tie, batch_size=20,
+                                  learning_rate=1e-3, dropout_prob=keep, weight_penalty=lam, activation_func=act,
+                                  loss_func='sigmoid_cross_entropy', weight_initialization='normal', verbose=False,
+                                  rng_mode='philox', precision=args.precision)
+        m.train(steps, record_every_nth=max(steps // 2, 1), save_every_nth=10 ** 9)
+        losses.append(m.get_performance_on_data(dl.val_X))
+        m.close()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    print(json.dumps({
+        'metric': 'MMAE hyper-parameter grid: 64 settings x %d train steps at batch 20, wall time' % steps,
+        'value': 64 * steps * 20 / dt, 'unit': 'samples/s', 'n_gpus': world, 'steps': steps, 'warmup': 0,
+        'ms_per_step': 1e3 * dt / (steps * ((64 + world - 1) // world)), 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'tf32', 'data': 'synthetic',
+        'config': {'workload': 'grid', 'settings': 64, 'steps_per_fit': steps, 'batch': 20,
+                   'grid': 'enc {[1000,100],[500,100],[300,100],[128,64]} x tie {T,F} x keep {1.0,0.5} x lambda {0,.001} x act {softsign,relu}',
+                   'parallelism': 'settings round-robin over %d GPU(s), no collective (generic_wrapper.py:246-256)' % world},
+        'grid_wall_s': dt, 'fits_per_s': 64 / dt, 'mean_val_loss_rank0': float(np.mean(losses)), 'gpu_launches': None}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='wide', choices=sorted(WORKLOADS) + ['grid'])
+    ap.add_argument('--precision', default='tf32', choices=['tf32', 'fp32'])
+    ap.add_argument('--rows', type=int, default=0, help='override the rows per step (infer / small)')
+    ap.add_argument('--grid-steps', type=int, default=300, help='train steps per setting of --workload grid')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-others', action='store_true', help='skip the short small / cls / infer legs of the default invocation')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    if args.workload == 'grid':
+        return run_grid(args, rank, world, local, dist)
+
+    name = args.workload
+    m = run_leg(name, args, rank, world, local, dist, args.steps, args.warmup, not args.no_e2e)
+    others = None
+    api = None
+    if world == 1 and name == 'wide' and not args.no_others and not args.rows:
+        others = {}
+        saved_rows = args.rows
+        for oname in ('small', 'cls', 'infer'):
+            try:
+                om = run_leg(oname, args, rank, world, local, None, 20, 5, False, clocks=False)
+                others[oname] = om
+            except Exception as e:          # a failed side leg must not take the headline line with it
+                others[oname] = {'error': repr(e)[:300]}
+        args.rows = saved_rows
+        try:
+            api = api_leg('wide', 5)
+        except Exception as e:
+            api = {'error': repr(e)[:300]}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peaks, pk = measured_peaks()
+    tf32_peak = measure_tf32_peak(torch)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         r = cpu_port_run(name, 3, 1, CPU_ROWS[name])
         cpu = {'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
                'noise_loop_share': r['noise_share']}
     line = {
-        'metric': METRIC[name], 'value': value, 'unit': 'samples/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'metric': METRIC[name], 'value': m['value'], 'unit': 'samples/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': m['ms'] / args.steps, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'tf32' if args.precision == 'tf32' else 'f32',
-        'data': 'synthetic',
-        'config': {'workload': name, 'global_batch': Bg, 'features': F, 'modality_blocks': len(w['blocks']),
-                   'encoder': w['layers'], 'head': head, 'loss': w['loss'], 'activation': w['act'],
-                   'parallelism': ('dp%d' % world) if train else ('rows sharded over %d GPU(s), no collective' % world),
-                   'l2_policy': 'inputs larger than L2 (batch X = %.2f GB per rank, re-read every step)' % (B * F * 4 / 1e9)
-                                if B * F * 4 > 126e6 else 'L2 flushed by the step itself: activations + deltas + Adam state written '
-                                                          'every step exceed nothing here; X = %.1f MB per rank stays L2-resident, '
-                                                          'as it would in a training loop over a resident dataset' % (B * F * 4 / 1e6),
-                   'noise': 'philox block-mask + 5% zero noise drawn on device every step' if train else
-                            'each modality block of each row missing (-1) with p = 0.2'},
-        'e2e': e2e, 'gpu_launches': launches, 'whole_network_launches': chains, 'graph_replays': replays, 'clocks': clocks, 'roofline': roofline,
-        'cpu_baseline': cpu,
+        'data': 'synthetic', 'config': config_of(m),
+        'e2e': m['e2e'], 'gpu_launches': m['launches'], 'whole_network_launches': m['chains'], 'graph_replays': m['replays'],
+        'clocks': m['clocks'], 'roofline': roofline_of(m, peaks, pk, tf32_peak), 'cpu_baseline': cpu,
     }
-    if train:
-        line['final_loss_per_sample'] = sc['recon_loss'] / Bg
+    if m['train']:
+        line['final_loss_per_sample'] = m['sc']['recon_loss'] / m['Bg']
+    if api is not None:
+        line['api'] = api
+    if others is not None:
+        line['others'] = {}
+        for oname, om in others.items():
+            if 'error' in om:
+                line['others'][oname] = om
+                continue
+            line['others'][oname] = {'metric': METRIC[oname], 'value': om['value'], 'unit': 'samples/s', 'ms_per_step': om['ms'] / om['steps'],
+                                     'steps': om['steps'], 'warmup': om['warmup'], 'config': config_of(om), 'gpu_launches': om['launches'],
+                                     'whole_network_launches': om['chains'], 'graph_replays': om['replays'],
+                                     'roofline': roofline_of(om, peaks, pk, tf32_peak)}
     print(json.dumps(line))
 
 

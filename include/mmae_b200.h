@@ -192,6 +192,9 @@ int mmae_apply_update(mmae_engine* e, int optimizer);
 /* ---- device-resident dataset + on-device batch sampling (data_funcs.py:161-195) ---- */
 int mmae_set_dataset(mmae_engine* e, int slot, const float* X_host, const float* Y_host,
                      int64_t rows, int32_t label_cols);
+/* mmae_set_dataset with the rows already in device memory (device-to-device copy into engine-owned buffers). */
+int mmae_set_dataset_device(mmae_engine* e, int slot, const float* X_dev, const float* Y_dev, int64_t rows, int32_t label_cols);
+
 /* A training VIEW of a resident dataset: the rows a cross-validation fold trains on (set_to_cross_validation_fold,
  * data_funcs.py:278-308) as a list of dataset rows.  The dataset is uploaded once; switching folds uploads count indices
  * instead of the matrix.  Sampled / given indices then address the view (index j = dataset row rows_host[j]).

@@ -75,6 +75,7 @@ PROTOTYPES = {
     'mmae_grad_buffer': (_I, [_P, C.POINTER(_P), C.POINTER(_L)]),
     'mmae_apply_update': (_I, [_P, _I]),
     'mmae_set_dataset': (_I, [_P, _I, _P, _P, _L, C.c_int32]),
+    'mmae_set_dataset_device': (_I, [_P, _I, _P, _P, _L, C.c_int32]),
     'mmae_set_dataset_view': (_I, [_P, _I, _P, _L]),
     'mmae_train_step_resident': (_I, [_P, _I, _P, _L, _I, _F, _I]),
     'mmae_modality_rmse': (_I, [_P, _P, _L, C.POINTER(C.c_double)]),

@@ -2018,6 +2018,27 @@ int mmae_set_dataset(mmae_engine* e, int slot, const float* X_host, const float*
   return 0;
 }
 
+int mmae_set_dataset_device(mmae_engine* e, int slot, const float* X_dev, const float* Y_dev, int64_t rows, int32_t label_cols) {
+  ENTER(e);
+  if (slot < 0 || slot > 1 || !X_dev || rows <= 0) return e->fail(MMAE_ERR_INVALID, "bad dataset arguments");
+  cudaError_t ce = cudaStreamSynchronize(e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "sync");
+  if (e->ds_X[slot]) { cudaFree(e->ds_X[slot]); e->ds_X[slot] = nullptr; }
+  if (e->ds_Y[slot]) { cudaFree(e->ds_Y[slot]); e->ds_Y[slot] = nullptr; }
+  if (e->ds_view[slot]) { cudaFree(e->ds_view[slot]); e->ds_view[slot] = nullptr; }
+  e->ds_view_rows[slot] = 0;
+  e->clear_graphs();
+  ce = cudaMalloc(&e->ds_X[slot], (size_t)rows * e->F * 4);
+  if (ce == cudaSuccess) ce = cudaMemcpy(e->ds_X[slot], X_dev, (size_t)rows * e->F * 4, cudaMemcpyDeviceToDevice);
+  if (ce == cudaSuccess && Y_dev && label_cols > 0) {
+    ce = cudaMalloc(&e->ds_Y[slot], (size_t)rows * label_cols * 4);
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->ds_Y[slot], Y_dev, (size_t)rows * label_cols * 4, cudaMemcpyDeviceToDevice);
+  }
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "set_dataset_device");
+  e->ds_rows[slot] = rows; e->ds_ycols[slot] = (Y_dev && label_cols > 0) ? label_cols : 0;
+  return 0;
+}
+
 int mmae_set_dataset_view(mmae_engine* e, int slot, const int64_t* rows_host, int64_t count) {
   ENTER(e);
   if (slot < 0 || slot > 1 || !e->ds_X[slot]) return e->fail(MMAE_ERR_STATE, "dataset slot is empty");

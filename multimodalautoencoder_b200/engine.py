@@ -427,6 +427,17 @@ class Engine:
             yp = Y.ctypes.data_as(C.c_void_p)
         self._ck(self.lib.mmae_set_dataset(self._h, slot, X.ctypes.data_as(C.c_void_p), yp, X.shape[0], yc))
 
+    def set_dataset_device(self, slot, X, Y=None):
+        """set_dataset from torch CUDA tensors (copied device-to-device into engine-owned buffers)."""
+        X = self._dev(X)
+        yc, yp = 0, None
+        if Y is not None:
+            self._check_labels(Y, X.shape[0])
+            Y = self._dev(Y)
+            yc = 1 if Y.dim() == 1 else Y.shape[1]
+            yp = C.c_void_p(Y.data_ptr())
+        self._ck(self.lib.mmae_set_dataset_device(self._h, slot, C.c_void_p(X.data_ptr()), yp, X.shape[0], yc))
+
     def set_dataset_view(self, slot, rows=None):
         """Training view of the resident dataset in `slot`: the dataset rows the current cross-validation fold trains on
         (None: all rows).  Sampled / given indices address the view."""

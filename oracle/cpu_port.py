@@ -28,8 +28,8 @@ class CpuPort:
         self.v = {k: torch.zeros_like(v) for k, v in self.P.items()}
         self.t = 0
 
-    def _act(self, z):
-        a = self.cfg.activation
+    def _act(self, z, a=None):
+        a = a or self.cfg.activation
         if a == 'relu':
             return torch.relu(z)
         if a == 'tanh':
@@ -112,13 +112,46 @@ class CpuPort:
         return O.fill_missing(self.cfg, np.asarray(X64, np.float64), Xbar), 0.0
 
     def cls_step(self, X64, Y64, rng=np.random):
-        """session.run([classification_opt_step]) (:647) on the fp64 oracle graph (NumPy BLAS threads): noise loop,
-        encoder + head forward, head loss, backward, second Adam.  Returns (loss, seconds in the noise loop)."""
-        if not hasattr(self, '_cls_state'):
-            self._cls_state = O.AdamState()
-            self._P64 = {k: v.detach().numpy().astype(np.float64) for k, v in self.P.items()}
+        """session.run([classification_opt_step]) (:647) in fp32 on torch's CPU kernels, like step(): noise loop, encoder
+        + head forward (:520-540 incl. the :533 activation bound), mean sigmoid-CE / sparse-softmax loss (:431-441),
+        reverse-mode gradients, the SECOND Adam (:443: own m / v / t; decoder untouched).
+        Returns (loss, seconds in the noise loop)."""
+        cfg, P = self.cfg, self.P
+        if not hasattr(self, '_m1'):
+            self._m1 = {k: torch.zeros_like(v) for k, v in P.items()}
+            self._v1 = {k: torch.zeros_like(v) for k, v in P.items()}
+            self._t1 = 0
         t0 = time.perf_counter()
-        noisy = O.add_noise(self.cfg, X64, rng)
+        noisy64 = O.add_noise(cfg, X64, rng)
         t_noise = time.perf_counter() - t0
-        c, _ = O.cls_train_step(self.cfg, self._P64, self._cls_state, noisy, Y64)
-        return float(c['cls_loss']) if 'cls_loss' in c else 0.0, t_noise
+        h = torch.from_numpy(np.asarray(noisy64, np.float32))
+        Y = torch.from_numpy(np.asarray(Y64, np.float32))
+        for i in range(cfg.L):
+            h = h @ P['weights%d' % i] + P['encode_biases%d' % i]
+            if i < cfg.L - 1:
+                h = self._act(h)
+        nh = len(cfg.head_dims())
+        for i in range(nh):
+            h = h @ P['classification_weights%d' % i] + P['classification_biases%d' % i]
+            if i < cfg.L - 1:                                   # :533
+                h = self._act(h, cfg.cls_activation)
+        if cfg.cls_loss == 'sigmoid_cross_entropy':
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(h, Y, reduction='mean')
+        else:
+            loss = torch.nn.functional.cross_entropy(h, Y.long(), reduction='mean')
+        if cfg.cls_weight_penalty:
+            loss = loss + cfg.cls_weight_penalty * sum(0.5 * (P['classification_weights%d' % i] ** 2).sum() for i in range(nh))
+        for p in P.values():
+            p.grad = None
+        loss.backward()
+        self._t1 += 1
+        a = cfg.cls_learning_rate * np.sqrt(1 - cfg.beta2 ** self._t1) / (1 - cfg.beta1 ** self._t1)
+        with torch.no_grad():
+            for k, p in P.items():
+                if p.grad is None:
+                    continue
+                g = p.grad
+                self._m1[k] += (g - self._m1[k]) * (1 - cfg.beta1)
+                self._v1[k] += (g * g - self._v1[k]) * (1 - cfg.beta2)
+                p -= a * self._m1[k] / (torch.sqrt(self._v1[k]) + cfg.adam_eps)
+        return float(loss.detach()), t_noise
