@@ -414,7 +414,7 @@ def roofline_of(m, peaks, pk, tf32_peak):
     if name in BYTES_PER_SAMPLE:      # small configs: the HBM bound beside the tensor bound (SURVEY 8d reports both)
         r['hbm_bound'] = {'algorithmic_GBps': BYTES_PER_SAMPLE[name] * value / world / 1e9, 'peak': peak_bw,
                           'frac': BYTES_PER_SAMPLE[name] * value / world / 1e9 / peak_bw}
-        r['binding_roof'] = 'tensor: 60 % of the HBM roof (%.2f G samples/s) lies above the tf32 compute bound (%.2f G samples/s)' % (
+        r['binding_roof'] = 'tensor: 60 %% of the HBM roof (%.2f G samples/s) lies above the tf32 compute bound (%.2f G samples/s)' % (
             0.6 * peak_bw / BYTES_PER_SAMPLE[name], tf32_peak * 1e3 / FLOPS_PER_SAMPLE[name]) if tf32_peak > 0 else None
     return r
 
@@ -556,7 +556,7 @@ def main():
                 others[oname] = {'error': repr(e)[:300]}
         args.rows = saved_rows
         try:
-            api = api_leg('wide', 5)
+            api = api_leg('wide', 10)
         except Exception as e:
             api = {'error': repr(e)[:300]}
     if dist is not None:

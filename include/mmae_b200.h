@@ -205,6 +205,10 @@ int mmae_set_dataset_view(mmae_engine* e, int slot, const int64_t* rows_host, in
 int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, int64_t batch,
                              int gen_noise, float keep, int classification);
 
+/* reconstruction_loss (:726) of a batch sampled on the device from a resident dataset (rows, noise and dropout as in
+ * mmae_train_step_resident, no update): the train-loss fetch of a record step without a host round trip. */
+int mmae_eval_resident(mmae_engine* e, int slot, int64_t batch, int gen_noise, float keep);
+
 /* ---- get_reconstruction_loss_per_modality (:1189-1216) as one batched pass: for every modality m the rows are
  *      reconstructed with block m set to the literal -1.0 (:1203) and rmse_host[m] receives sqrt(mean((X - X_hat)^2)) over
  *      that block's columns.  The M masked copies are stacked into one batch per chunk of rows (one forward for all

@@ -78,6 +78,7 @@ PROTOTYPES = {
     'mmae_set_dataset_device': (_I, [_P, _I, _P, _P, _L, C.c_int32]),
     'mmae_set_dataset_view': (_I, [_P, _I, _P, _L]),
     'mmae_train_step_resident': (_I, [_P, _I, _P, _L, _I, _F, _I]),
+    'mmae_eval_resident': (_I, [_P, _I, _L, _I, _F]),
     'mmae_modality_rmse': (_I, [_P, _P, _L, C.POINTER(C.c_double)]),
     'mmae_read_scalars': (_I, [_P, C.POINTER(C.c_double), _I]),
     'mmae_comm_unique_id': (_I, [_P]),

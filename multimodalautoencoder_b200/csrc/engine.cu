@@ -2159,6 +2159,33 @@ int mmae_modality_rmse(mmae_engine* e, const float* X_host, int64_t rows, double
   return rc;
 }
 
+int mmae_eval_resident(mmae_engine* e, int slot, int64_t batch, int gen_noise, float keep) {
+  ENTER(e);
+  if (slot < 0 || slot > 1 || !e->ds_X[slot]) return e->fail(MMAE_ERR_STATE, "dataset slot is empty");
+  if (e->sticky) return e->fail(MMAE_ERR_CUDA, "engine is in a sticky CUDA error state: " + e->err);
+  int r = e->ensure_resident(batch); if (r) return r;
+  const int64_t* view = e->ds_view[slot];
+  const uint32_t n_rows = (uint32_t)(view ? e->ds_view_rows[slot] : e->ds_rows[slot]);
+  bool noisy_ready = false;
+  if (gen_noise && noise_materialises(e, batch)) {
+    r = launch_sample_noise(e, e->ds_X[slot], n_rows, nullptr, batch, e->first_row, e->gxb, view); if (r) return r;
+    noisy_ready = true;
+  } else {
+    philox_indices_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, e->stream>>>(e->d_idx, batch, e->first_row, n_rows, &e->d_state->step,
+                                                                                e->cfg.seed, nullptr, view);
+    gather_rows_kernel<<<(unsigned)((batch + 7) / 8), 256, 0, e->stream>>>(e->ds_X[slot], e->d_idx, e->gxb, batch, e->F);
+    e->launches += 2;
+    if (gen_noise) { r = launch_noise_gen(e, batch, e->first_row); if (r) return r; }
+  }
+  r = e->begin_step(batch, gen_noise != 0); if (r) return r;
+  mmae_engine::FwdOpts o; o.X = e->gxb; o.target = e->gxb; o.labels = nullptr; o.B = batch; o.noise = gen_noise != 0; o.keep = keep;
+  o.train_recon = false; o.decoder = true; o.headp = false; o.recon_out = nullptr; o.need_mu = false; o.noisy_ready = noisy_ready;
+  r = e->forward(o); if (r) return r;
+  r = e->finalize_scalars(batch, true, false); if (r) return r;
+  e->last_B = batch;
+  return e->advance_step();
+}
+
 int mmae_read_scalars(mmae_engine* e, double* out, int count) {
   ENTER(e);
   if (!out || count <= 0 || count > MMAE_NUM_SCALARS) return e->fail(MMAE_ERR_INVALID, "bad scalar count");

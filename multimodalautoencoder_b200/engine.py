@@ -455,6 +455,10 @@ class Engine:
         self._ck(self.lib.mmae_train_step_resident(self._h, slot, ip, int(batch), int(bool(gen_noise)), float(keep),
                                                    int(bool(classification))))
 
+    def eval_resident(self, slot, batch, gen_noise=True, keep=1.0):
+        """reconstruction_loss of a batch sampled on the device from the resident dataset (no update); read it with scalars()."""
+        self._ck(self.lib.mmae_eval_resident(self._h, slot, int(batch), int(bool(gen_noise)), float(keep)))
+
     def modality_rmse(self, X_host):
         """get_reconstruction_loss_per_modality (:1189-1216) in one batched device pass: list of M RMSE values."""
         X = np.ascontiguousarray(X_host, np.float32)

@@ -383,12 +383,14 @@ class MultimodalAutoencoder:
                     self.train_acc.append(ta); self.val_acc.append(va)
                     self.classification_train_loss.append(tl); self.classification_val_loss.append(vl)
                 else:
-                    X = dl.get_unsupervised_train_batch(B)
-                    tl = self._loss_on(X, noise=True, keep=keep)
+                    # train loss: a batch sampled, noised and evaluated on the device (the training matrix is resident)
+                    eng.set_rng_step(self._next_rng_step())
+                    eng.eval_resident(slot, B, gen_noise=True, keep=keep)
+                    tl = eng.scalars()['recon_loss']
                     val_X = dl.get_unsupervised_val_batch(200)
                     vl = self._loss_on(val_X, noise=True)
                     if 'entropy' in self.loss_func:
-                        tl, vl = tl / len(X), vl / len(val_X)
+                        tl, vl = tl / B, vl / len(val_X)
                     self.train_loss.append(tl); self.val_loss.append(vl)
                 if self.verbose:
                     print("Training iteration", step, "\t train", tl, "\t validation", vl)
