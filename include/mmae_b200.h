@@ -81,6 +81,11 @@ typedef struct {
   uint64_t seed;                     /* Philox key                                          */
   int32_t precision;                 /* mmae_precision                                      */
   int64_t max_batch;                 /* workspace hint; grown on demand                     */
+  /* comparison_algorithms/neural_net.py on the same kernels: a plain MLP classifier = the encoder stack
+   * with EVERY layer activated (+ dropout) followed by one linear logits layer (the head, num_head_layers == 1), no
+   * decoder in the loss; trained by the head optimizer with head_weight_penalty on every weight matrix (:181-182). */
+  int32_t classifier_only;
+  float clip_norm;                   /* > 0: tf.clip_by_global_norm(gradients, clip_norm) before Adam (:189-190)  */
 } mmae_config;
 
 /* Bits of `want` for mmae_forward */

@@ -36,6 +36,7 @@ class Config(C.Structure):
         ('num_noise_types', C.c_int32), ('noise_type_masks', C.POINTER(C.c_uint32)),
         ('noise_thresholds', C.POINTER(C.c_uint32)), ('num_modalities_to_drop', C.c_int32),
         ('seed', C.c_uint64), ('precision', C.c_int32), ('max_batch', C.c_int64),
+        ('classifier_only', C.c_int32), ('clip_norm', C.c_float),
     ]
 
 

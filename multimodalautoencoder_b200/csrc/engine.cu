@@ -256,6 +256,7 @@ struct mmae_engine {
       if (c->num_noise_types > 1) thresholds.assign(c->noise_thresholds, c->noise_thresholds + c->num_noise_types - 1);
     }
     E = layers[L - 1]; C = H > 0 ? head[H - 1] : 0;
+    if (c->classifier_only && (H != 1 || c->variational)) return fail(MMAE_ERR_INVALID, "classifier_only needs exactly one (logits) head layer and no VAE");
     cfg.modality_starts = nullptr; cfg.layer_sizes = nullptr; cfg.head_sizes = nullptr;
     cfg.noise_type_masks = nullptr; cfg.noise_thresholds = nullptr;
 
@@ -282,7 +283,7 @@ struct mmae_engine {
       snprintf(buf, 64, "decode_biases%d", i); add_var(buf, enc_in(i), 0, 0, 0.f, 0.f);
     }
     for (int i = 0; i < L; ++i) {
-      snprintf(buf, 64, "weights%d", i); add_var(buf, enc_in(i), layers[i], 1, tied ? 2.f * lam : lam, 0.f);
+      snprintf(buf, 64, "weights%d", i); add_var(buf, enc_in(i), layers[i], 1, tied ? 2.f * lam : lam, c->classifier_only ? lamc : 0.f);
       snprintf(buf, 64, "encode_biases%d", i); add_var(buf, layers[i], 0, 1, 0.f, 0.f);
     }
     if (c->variational) {
@@ -873,6 +874,7 @@ struct mmae_engine {
       Epilogue e = epi(EPI_BIAS_ACT); e.bias = pvar(bn);
       float* dst;
       if (!last) { e.act = act; if (o.keep < 1.f) set_dropout(e, o.keep, (uint32_t)i, dout); dst = ea[i]; }
+      else if (cfg.classifier_only) { e.act = act; if (o.keep < 1.f) set_dropout(e, o.keep, (uint32_t)i, dout); dst = mu; }   // neural_net.py:157-167
       else { e.act = MMAE_ACT_LINEAR; dst = mu; }
       RET(gemm(false, false, B, dout, din, a, lda, pvar(wn), dout, dst, dout, lnv, e, nullptr, false));
       a = dst; lda = dout;
@@ -923,7 +925,7 @@ struct mmae_engine {
         const int din = i == 0 ? E : head[i - 1], dout = head[i];
         char wn[40], bn[40]; snprintf(wn, 40, "classification_weights%d", i); snprintf(bn, 40, "classification_biases%d", i);
         Epilogue e = epi(EPI_BIAS_ACT); e.bias = pvar(bn);
-        const bool activated = i < L - 1;                   // reference quirk: bound is the AE depth (:533)
+        const bool activated = !cfg.classifier_only && i < L - 1;   // reference quirk: bound is the AE depth (:533); the plain MLP's logits are linear
         if (activated) { e.act = cfg.head_activation; if (o.keep < 1.f) set_dropout(e, o.keep, 64u + (uint32_t)i, dout); }
         else e.act = MMAE_ACT_LINEAR;
         float* dst = (i == H - 1) ? hlogits : ha[i];
@@ -1231,7 +1233,7 @@ struct mmae_engine {
     d_fused = false;
     float* d = hdelta; int64_t ldd = C;
     float* nxt = dA;
-    if (H - 1 < L - 1) {     // quirk (:533): the logits themselves went through act + dropout
+    if (!cfg.classifier_only && H - 1 < L - 1) {     // quirk (:533): the logits themselves went through act + dropout
       // d <- d * act'(logits) * dropmask/keep, done by a 1-column-block "GEMM-free" pass: reuse the dgrad epilogue
       Epilogue ed = epi(EPI_DGRAD); ed.saved = hlogits; ed.lds = C; ed.act = cfg.head_activation;
       if (keep < 1.f) set_dropout(ed, keep, 64u + (uint32_t)(H - 1), C);
@@ -1246,7 +1248,7 @@ struct mmae_engine {
       Epilogue ew = epi(EPI_PLAIN);
       RET(gemm(true, false, din, dout, B, u_in, din, d, ldd, gvar(wn), dout, noise_view(false), ew, nullptr, true));
       RET(bucket_vars(wn, bn));
-      const bool act_prev = i > 0 && (i - 1) < L - 1;
+      const bool act_prev = !cfg.classifier_only && i > 0 && (i - 1) < L - 1;
       Epilogue ed = epi(act_prev ? EPI_DGRAD : EPI_PLAIN);
       if (act_prev) { ed.saved = ha[i - 1]; ed.lds = din; ed.act = cfg.head_activation; if (keep < 1.f) set_dropout(ed, keep, 64u + (uint32_t)(i - 1), din); }
       ed.colsum_partials = colpart;
@@ -1258,6 +1260,13 @@ struct mmae_engine {
     if (cfg.variational) {
       vae_grad_kernel<<<grid_for(B * E, 256), 256, 0, stream>>>(d, glv, emb, lv, eps, B * E, 0.f);
       CKL("vae_grad");
+      d_fused = false;
+    }
+    if (cfg.classifier_only) {      // the last hidden layer is activated too: back through act' (and its dropout mask)
+      Epilogue ed = epi(EPI_DGRAD); ed.saved = mu; ed.lds = E; ed.act = cfg.activation;
+      if (keep < 1.f) set_dropout(ed, keep, (uint32_t)(L - 1), E);
+      elementwise_epilogue_kernel<<<grid_for(B * E, 256), 256, 0, stream>>>(d, B, E, ed);
+      CKL("embedding_act_grad");
       d_fused = false;
     }
     return backward_encoder(B, d, keep);
@@ -1371,6 +1380,14 @@ struct mmae_engine {
     a.begin = b; a.end = e;
     a.segs = d_segs[opt]; a.nsegs = nsegs[opt]; a.sums = d_sums;
     a.scale_mode = (opt == 0 && cfg.loss_func == MMAE_LOSS_RMSE) ? 1 : 0;
+    a.clip_norm = cfg.clip_norm;
+    if (opt == 1 && cfg.clip_norm > 0.f) {        // tf.clip_by_global_norm over every gradient of the step (incl. the L2 term)
+      const int g = (int)std::min<int64_t>(num_sms * 2, (e - b + 255) / 256);
+      grad_sqnorm_kernel<<<g, 256, 0, st>>>(P, G, b, e, d_segs[opt], nsegs[opt], partials);
+      CKL("grad_sqnorm");
+      reduce_partials_kernel<<<1, 256, 0, st>>>(partials, g, d_sums + 6, 0); CKL("reduce_partials");
+      a.scale_mode = 2;
+    }
     a.n_elems = (double)gbatch(B) * F;
     a.alpha = &d_state->alpha[opt];
     a.b1 = cfg.beta1; a.b2 = cfg.beta2; a.eps = cfg.adam_eps; a.scalars_out = d_scalars;

@@ -412,7 +412,8 @@ struct AdamArgs {
   int64_t begin, end;            // flat range inside P / G;  M, V are indexed from 0 at `begin`
   const AdamSeg* segs; int nsegs;
   const double* sums;            // device scalars (loss sums after the optional allreduce)
-  int scale_mode;                // 0: 1.0   1: RMSE 1/sqrt(N*sumsq), N = n_elems
+  int scale_mode;                // 0: 1.0   1: RMSE 1/sqrt(N*sumsq), N = n_elems   2: clip_by_global_norm (sums[6] = ||g||^2)
+  float clip_norm;
   double n_elems;
   const float* alpha;            // lr * sqrt(1 - b2^t) / (1 - b1^t), written by adam_prep_kernel for this step
   float b1, b2, eps;
@@ -422,6 +423,8 @@ struct AdamArgs {
 __global__ void adam_kernel(const AdamArgs a) {
   float scale = 1.f;
   if (a.scale_mode == 1) scale = (float)(1.0 / sqrt(a.n_elems * a.sums[0]));
+  float clip = 1.f;              // tf.clip_by_global_norm: g * clip_norm / max(||g||, clip_norm), g INCLUDING the L2 term
+  if (a.scale_mode == 2) { const double nrm = sqrt(a.sums[6]); clip = (float)((double)a.clip_norm / fmax(nrm, (double)a.clip_norm)); }
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.scalars_out) a.scalars_out[MMAE_S_GRAD_SCALE] = scale;
   const float alpha = __ldg(a.alpha);
   int64_t n = a.end - a.begin;
@@ -430,7 +433,7 @@ __global__ void adam_kernel(const AdamArgs a) {
     int lo = 0, hi = a.nsegs - 1;                 // last segment with begin <= gi
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (a.segs[mid].begin <= gi) lo = mid; else hi = mid - 1; }
     float p = a.P[gi];
-    float g = scale * a.G[gi] + a.segs[lo].l2 * p;
+    float g = (scale * a.G[gi] + a.segs[lo].l2 * p) * clip;
     float m = a.M[i], v = a.V[i];
     m += (g - m) * (1.f - a.b1);
     v += (g * g - v) * (1.f - a.b2);
@@ -445,6 +448,27 @@ __global__ void adam_kernel(const AdamArgs a) {
         a.PT[a.segs[lo].begin + (int64_t)c * rows + r] = pn;
       }
     }
+  }
+}
+
+// ||G + l2 * P||^2 over [begin, end): per-block partials (fixed order), summed by reduce_partials_kernel into sums[6]
+__global__ void grad_sqnorm_kernel(const float* __restrict__ P, const float* __restrict__ G, int64_t begin, int64_t end,
+                                   const AdamSeg* __restrict__ segs, int nsegs, float* __restrict__ partials) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int64_t gi = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < end; gi += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = nsegs - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (segs[mid].begin <= gi) lo = mid; else hi = mid - 1; }
+    const float g = G[gi] + segs[lo].l2 * P[gi];
+    acc += g * g;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    partials[blockIdx.x] = t;
   }
 }
 

@@ -45,6 +45,8 @@ class EngineConfig:
     seed: int = 0
     precision: str = 'tf32'
     max_batch: int = 256
+    classifier_only: bool = False        # comparison_algorithms/neural_net.py: plain MLP classifier (every hidden layer activated)
+    clip_norm: float = 0.0               # > 0: tf.clip_by_global_norm(gradients, clip_norm) in the head optimizer
 
     def head_widths(self):
         if self.cls_layer_sizes is None:
@@ -108,6 +110,8 @@ class Engine:
         c.seed = cfg.seed
         c.precision = capi.PREC[cfg.precision]
         c.max_batch = cfg.max_batch
+        c.classifier_only = int(cfg.classifier_only)
+        c.clip_norm = float(cfg.clip_norm)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             rc = self.lib.mmae_create(C.byref(c), C.byref(h))

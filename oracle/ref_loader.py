@@ -49,8 +49,8 @@ def _stub_matplotlib():
 
 
 class Reference:
-    def __init__(self, tf, mmae, data_funcs):
-        self.tf, self.mmae, self.data_funcs = tf, mmae, data_funcs
+    def __init__(self, tf, mmae, data_funcs, neural_net=None):
+        self.tf, self.mmae, self.data_funcs, self.neural_net = tf, mmae, data_funcs, neural_net
 
     def make_loader(self, train_X, val_X, modality_starts, modality_names, train_Y=None, val_Y=None, num_labels=None,
                     test_X=None, test_Y=None):
@@ -70,6 +70,9 @@ class Reference:
         dl.wanted_labels = []
         dl.fold = None
         return dl
+
+    def nn_variables(self, model):
+        return {v.name: v for v in model.graph.variables if v.name and v.name != 'global_step'}
 
     @staticmethod
     def variables(model):
@@ -95,7 +98,7 @@ def load_reference(dtype=None):
             sys.path.pop(0)
         if not build_ref.build():
             return None
-        saved = {k: sys.modules.get(k) for k in ('tensorflow', 'matplotlib', 'matplotlib.pyplot', 'data_funcs', 'helper_funcs')}
+        saved = {k: sys.modules.get(k) for k in ('tensorflow', 'matplotlib', 'matplotlib.pyplot', 'data_funcs', 'helper_funcs', 'generic_wrapper')}
         tf = _load_module('mmae_tf1_shim', os.path.join(SHIM_DIR, 'tensorflow', '__init__.py'))
         try:
             sys.modules['tensorflow'] = tf
@@ -108,13 +111,20 @@ def load_reference(dtype=None):
             df = _load_module('mmae_ref_data_funcs', os.path.join(REF_DIR, 'data_funcs.py'))
             sys.modules['data_funcs'] = df
             mm = _load_module('mmae_ref_multimodal_autoencoder', os.path.join(REF_DIR, 'multimodal_autoencoder.py'))
+            nn = None
+            try:       # the plain MLP classifier (comparison_algorithms/neural_net.py) and what it imports
+                sys.modules['helper_funcs'] = _load_module('mmae_ref_helper_funcs', os.path.join(REF_DIR, 'helper_funcs.py'))
+                sys.modules['generic_wrapper'] = _load_module('mmae_ref_generic_wrapper', os.path.join(REF_DIR, 'generic_wrapper.py'))
+                nn = _load_module('mmae_ref_neural_net', os.path.join(REF_DIR, 'neural_net.py'))
+            except Exception as e:       # noqa: BLE001 -- the MMAE pinning does not depend on it
+                print('oracle/_ref: neural_net.py not loadable:', repr(e)[:200])
         finally:
             for k, v in saved.items():          # leave no fake `tensorflow` / `matplotlib` behind for other importers
                 if v is None:
                     sys.modules.pop(k, None)
                 else:
                     sys.modules[k] = v
-        _cached = Reference(tf, mm, df)
+        _cached = Reference(tf, mm, df, nn)
     if dtype is not None:
         _cached.tf.set_default_dtype(dtype)
     return _cached

@@ -386,7 +386,11 @@ nn = _NN()
 
 
 # ----------------------------------------------------------------------------- training
-class _MinimizeOp(Tensor):
+class _SideEffectOp(Tensor):
+    """Ops that assign variables: Session.run evaluates them after every plain fetch of the same run."""
+
+
+class _MinimizeOp(_SideEffectOp):
     def __init__(self, opt, loss, var_list):
         super().__init__(None, (), 'minimize')
         self.opt, self.loss, self.var_list = opt, loss, var_list
@@ -396,6 +400,59 @@ class _MinimizeOp(Tensor):
         if k not in ctx.cache:
             ctx.cache[k] = self.opt._apply(self.loss, self.var_list, ctx)
         return None
+
+
+class _ApplyGradientsOp(_SideEffectOp):
+    def __init__(self, opt, grads_and_vars, global_step):
+        super().__init__(None, (), 'apply_gradients')
+        self.opt, self.gv, self.global_step = opt, list(grads_and_vars), global_step
+
+    def _eval(self, ctx):
+        k = id(self)
+        if k not in ctx.cache:
+            grads = [g._eval(ctx) if isinstance(g, Tensor) else g for g, _ in self.gv]
+            self.opt._adam([v for _, v in self.gv], grads, ctx)
+            if self.global_step is not None:
+                self.global_step.value = self.global_step.value + 1
+            ctx.cache[k] = True
+        return None
+
+
+class _GradBundle(Tensor):
+    """d loss / d params for a list of variables: one autograd pass shared by the per-variable gradient nodes."""
+
+    def __init__(self, loss, params):
+        super().__init__(None, (), 'gradients')
+        self.loss, self.params = loss, list(params)
+
+    def _eval(self, ctx):
+        k = id(self)
+        if k not in ctx.cache:
+            leaves = {v: v.value.detach().clone().requires_grad_(True) for v in self.params}
+            c2 = _Ctx(ctx.feeds, leaves)
+            c2.rand = ctx.rand
+            lv = self.loss._eval(c2)
+            gs = torch.autograd.grad(lv, [leaves[v] for v in self.params], allow_unused=True)
+            ctx.cache[k] = [None if g is None else g.detach() for g in gs]
+        return ctx.cache[k]
+
+
+def gradients(ys, xs, name=None):
+    b = _GradBundle(ys, xs)
+    return [Tensor(lambda ctx, bundle, i=i: bundle[i], (b,)) for i in range(len(b.params))]
+
+
+def clip_by_global_norm(t_list, clip_norm, name=None):
+    """t_list[i] * clip_norm / max(global_norm, clip_norm), global_norm = sqrt(sum ||t||^2)."""
+    def norm_fn(ctx, *ts):
+        return torch.sqrt(sum((t * t).sum() for t in ts if t is not None))
+    norm = Tensor(norm_fn, tuple(t_list), 'global_norm')
+    outs = [Tensor(lambda ctx, t, n: None if t is None else t * (clip_norm / torch.clamp(n, min=float(clip_norm))), (t, norm)) for t in t_list]
+    return outs, norm
+
+
+def trainable_variables():
+    return [v for v in _current_graph().variables if v.trainable]
 
 
 class _Train:
@@ -420,6 +477,26 @@ class _Train:
             if var_list is None:
                 var_list = list(self.graph.variables)       # default: every trainable variable of the graph
             return _MinimizeOp(self, loss, var_list)
+
+        def apply_gradients(self, grads_and_vars, global_step=None, name=None):
+            return _ApplyGradientsOp(self, grads_and_vars, global_step)
+
+        def _adam(self, variables, grads, ctx):
+            lr = self.lr._eval(_Ctx(ctx.feeds)) if isinstance(self.lr, Tensor) else self.lr
+            alpha = float(lr) * math.sqrt(1.0 - self.b2_power) / (1.0 - self.b1_power)
+            self.last_grads = {}
+            with torch.no_grad():
+                for v, g in zip(variables, grads):
+                    if g is None:
+                        continue
+                    self.last_grads[v.name] = g.detach().cpu().numpy().copy()
+                    m = self.m.setdefault(v, torch.zeros_like(v.value))
+                    s = self.v.setdefault(v, torch.zeros_like(v.value))
+                    m += (g - m) * (1.0 - self.b1)
+                    s += (g * g - s) * (1.0 - self.b2)
+                    v.value = v.value - alpha * m / (torch.sqrt(s) + self.eps)
+            self.b1_power *= self.b1
+            self.b2_power *= self.b2
 
         def _apply(self, loss, var_list, ctx):
             cand = [v for v in var_list if v.trainable and v.value is not None and v.value.dtype.is_floating_point]
@@ -466,6 +543,10 @@ class _Train:
     def get_checkpoint_state(directory):
         return None
 
+    @staticmethod
+    def latest_checkpoint(directory):
+        return None
+
 
 train = _Train()
 
@@ -479,12 +560,12 @@ class Session:
         single = not isinstance(fetches, (list, tuple))
         fl = [fetches] if single else list(fetches)
         # ops with side effects (minimize) see the pre-update variables, like every other fetch of the run
-        plain = [f for f in fl if not isinstance(f, _MinimizeOp)]
+        plain = [f for f in fl if not isinstance(f, _SideEffectOp)]
         vals = {}
         for f in plain:
             vals[id(f)] = _out(f._eval(ctx)) if isinstance(f, Tensor) else f
         for f in fl:
-            if isinstance(f, _MinimizeOp):
+            if isinstance(f, _SideEffectOp):
                 f._eval(ctx)
                 vals[id(f)] = None
         out = [vals[id(f)] for f in fl]
