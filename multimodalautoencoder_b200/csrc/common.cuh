@@ -120,6 +120,8 @@ struct Epilogue {
   // loss modes
   const float* target;    // [M, ldt]
   int64_t ldt;
+  const int64_t* aux_rows; // optional (row-layout tcgen05 epilogue only): row r of the target is target[aux_rows[r]] -- the loss
+                          // reads its clean rows straight from a resident dataset through the sampled index list
   int loss;               // mmae_loss
   float* loss_partials;   // one float per CTA (deterministic two-stage reduction), may be null
   float* colsum_partials; // tcgen05 family only: [ceil(M/32), N] column sums of the stored values per 32-row group

@@ -539,6 +539,16 @@ struct mmae_engine {
     if (pending_loss_partials > 0) { int64_t n = pending_loss_partials; pending_loss_partials = 0; return reduce_partials(n, 0); }
     return 0;
   }
+  // The reconstruction-loss GEMM of a resident-dataset step can read its clean target rows through the sampled index
+  // list when it runs on the two-SM kernel with the row-layout epilogue (wide models): no clean copy of the batch.
+  bool final_gemm_gathers_target(int64_t B, float keep) const {
+    static const bool off = (getenv("MMAE_TMA_EPI") && getenv("MMAE_TMA_EPI")[0] == '0') || (getenv("MMAE_TC2") && getenv("MMAE_TC2")[0] == '0') ||
+                            (getenv("MMAE_GATHER_TARGET") && getenv("MMAE_GATHER_TARGET")[0] == '0');
+    const int k_last = layers[0];
+    // (F > 512 also rules out the whole-network kernel, whose TMA-loaded target tile cannot gather rows)
+    return !off && cfg.precision == MMAE_PREC_TF32 && !cfg.variational && keep >= 1.f && B >= 256 && F > 512 && (F & 3) == 0 &&
+           k_last >= 32 && (k_last & 3) == 0;
+  }
   float* wg_ws = nullptr; int64_t wg_ws_cap = 0;
   int64_t wgroup_launches = 0;
 
@@ -559,6 +569,7 @@ struct mmae_engine {
         if (wt) { g.B = wt; g.ldb = k; tb = true; }
       }
       const bool two_sm = tc2_eligible(ta, tb, g);       // 256 x 256 tiles on CTA pairs (cta_group::2)
+      if (ep.aux_rows && !two_sm) return fail(MMAE_ERR_STATE, "internal: gathered loss target outside the two-SM row-layout epilogue");
       if (nv.enabled && !two_sm) return fail(MMAE_ERR_STATE, "internal: noisy operand reached the one-SM tcgen05 GEMM");
       if (nv.enabled) ++fused_noise_launches;
       const int max_s = allow_splitk && ep.mode == EPI_PLAIN ? 64 : 1;
@@ -583,6 +594,7 @@ struct mmae_engine {
       if (n_partials) *n_partials = pl.grid;
       return 0;
     }
+    if (ep.aux_rows) return fail(MMAE_ERR_STATE, "internal: gathered loss target reached the CUDA-core GEMM");
     g.ep.colsum_partials = nullptr;
     g.splits = 1; g.k_per_split = 0; g.ws = nullptr; g.tile_counters = nullptr;
     {      // in-kernel split-K (any epilogue): the last CTA of a tile reduces the slices and finishes the tile
@@ -640,6 +652,7 @@ struct mmae_engine {
     float* fill_out = nullptr;     // whole-network kernel: write the filled matrix (A15) instead of decoded_X
     bool need_mu = true;           // the embedding is wanted in global memory (it is not for plain predict / fill-in)
     bool noisy_ready = false;      // `noisy` already holds the noisy batch of X (sample_noise_kernel drew and applied it)
+    const int64_t* target_rows = nullptr;   // the loss target is target[target_rows[r]] (rows of a resident dataset; no clean copy of the batch)
   };
 
   int begin_step(int64_t B, bool noise) {
@@ -910,6 +923,7 @@ struct mmae_engine {
         } else {
           e = epi(o.train_recon ? EPI_LOSS_TRAIN : EPI_LOSS_PRED); e.bias = pvar(bn); e.loss = cfg.loss_func;
           e.target = o.target; e.ldt = F; e.loss_partials = o.target ? partials : nullptr;
+          e.aux_rows = o.target_rows;
           if (o.train_recon) e.colsum_partials = colpart;
           dst = o.recon_out ? o.recon_out : out;
           RET(gemm(false, tb, B, dout, din, u, ldu, W, ldw, dst, dout, noise_view(false), e, &np, false));
@@ -1501,7 +1515,7 @@ int launch_sample_noise(mmae_engine* e, const float* src, uint32_t n_rows, const
 }
 
 int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float keep, const float* target = nullptr, bool defer_advance = false,
-             bool noisy_ready = false) {
+             bool noisy_ready = false, const int64_t* target_rows = nullptr) {
   if (use_noise == 3 && !noisy_ready) {
     if (e->sticky) return e->fail(MMAE_ERR_CUDA, "engine is in a sticky CUDA error state: " + e->err);
     int r0 = e->ensure_cap(B); if (r0) return r0;
@@ -1513,6 +1527,7 @@ int do_train(mmae_engine* e, const float* X, int64_t B, int use_noise, float kee
   mmae_engine::FwdOpts o; o.X = X; o.target = target ? target : X; o.labels = nullptr; o.B = B; o.noise = use_noise != 0; o.keep = keep;
   o.noisy_ready = noisy_ready;
   o.train_recon = true; o.decoder = true; o.headp = false; o.recon_out = nullptr;
+  o.target_rows = target_rows;
   r = e->forward(o); if (r) return r;
   r = e->sums_allreduce(); if (r) return r;          // overlaps the whole backward pass
   r = e->backward_recon(B, keep); if (r) return r;
@@ -1817,11 +1832,12 @@ int mmae_apply_update(mmae_engine* e, int optimizer) {
 }
 
 namespace {
-int train_core(mmae_engine* e, const float* Xd, const float* target, int64_t batch, int use_noise, float keep, bool noisy_ready = false) {
+int train_core(mmae_engine* e, const float* Xd, const float* target, int64_t batch, int use_noise, float keep, bool noisy_ready = false,
+               const int64_t* target_rows = nullptr) {
   e->fast_step = !e->dp_on(); e->step_finalized = false; e->pending_loss_partials = 0;
   int r = e->begin_dp_pipeline(0, batch); if (r) return r;
   const bool piped = e->dp_pipeline;
-  r = do_train(e, Xd, batch, use_noise, keep, target, true, noisy_ready);
+  r = do_train(e, Xd, batch, use_noise, keep, target, true, noisy_ready, target_rows);
   e->fast_step = false;
   if (r) { e->dp_pipeline = false; return r; }
   r = e->flush_pending_loss(); if (r) return r;
@@ -2108,9 +2124,13 @@ int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, 
       ce = cudaMemcpyAsync(e->d_idx_in, idx_host, (size_t)batch * 8, cudaMemcpyHostToDevice, e->stream);
       if (ce != cudaSuccess) return e->cuda_fail(ce, "H2D indices");
     }
+    bool gather_target = false;
     if (gen_noise && noise_materialises(e, batch)) {
-      // one kernel: Philox row indices (or the given ones), fold view, gather of the clean batch, descriptor, noisy batch
-      int rr = launch_sample_noise(e, e->ds_X[slot], n_rows, idx_host ? e->d_idx_in : nullptr, batch, e->first_row, e->gxb, view);
+      // one kernel: Philox row indices (or the given ones), fold view, gather of the clean batch, descriptor, noisy batch.
+      // Wide models skip the clean copy: their loss GEMM reads the target rows of the dataset through the index list.
+      gather_target = !classification && e->final_gemm_gathers_target(batch, keep);
+      int rr = launch_sample_noise(e, e->ds_X[slot], n_rows, idx_host ? e->d_idx_in : nullptr, batch, e->first_row,
+                                   gather_target ? nullptr : e->gxb, view);
       if (rr) return rr;
       noisy_ready = true;
     } else {
@@ -2127,6 +2147,7 @@ int mmae_train_step_resident(mmae_engine* e, int slot, const int64_t* idx_host, 
     }
     ce = cudaGetLastError();
     if (ce != cudaSuccess) return e->cuda_fail(ce, "gather");
+    if (gather_target) return train_core(e, e->ds_X[slot], nullptr, batch, 1, keep, true, e->d_idx);
     return classification ? cls_core(e, e->gxb, e->gyb, batch, gen_noise ? 1 : 0, keep, noisy_ready)
                           : train_core(e, e->gxb, nullptr, batch, gen_noise ? 1 : 0, keep, noisy_ready);
   };

@@ -283,6 +283,7 @@ inline cudaError_t launch_gemm_tc2(bool ta, bool tb, const GemmArgs& g, const Tc
     const bool aux_ok = !auxp || ((ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(auxp) & 15) == 0);
     if (aux_ok && make_tmap_io(&p.tmC, p.C, g.M, g.N, p.ldc)) p.tma_epi = 1;
   }
+  if (p.ep.aux_rows && !p.tma_epi) return cudaErrorInvalidValue;      // only the row-layout epilogue gathers its target rows
   return tc2_launch(a_mn, b_mn, g.noise.enabled != 0, p, pl.grid, st);
 }
 

@@ -105,17 +105,19 @@ struct RtAux { float4 v[8]; };
 // Auxiliary values (loss target / saved activation) of the 32 x 32 chunk at (row0, col0), COALESCED: load i of lane l
 // covers row row0 + l/8 + 4i, columns col0 + 4 (l%8) .. +3, so every instruction reads four full 128-byte row segments.
 // The values reach the row-per-thread layout through the warp's shared-memory tile (rt_stage_aux).
-__device__ __forceinline__ void rt_load_aux(const float* auxp, int64_t ldaux, int64_t row0, int64_t M, int64_t col0, int64_t N, int lane, RtAux& ax) {
+__device__ __forceinline__ void rt_load_aux(const float* auxp, int64_t ldaux, int64_t row0, int64_t M, int64_t col0, int64_t N, int lane, RtAux& ax,
+                                            const int64_t* aux_rows = nullptr) {
   const int q = lane & 7;
   const bool col_ok = auxp != nullptr && col0 + q * 4 < N;
   const float* sp = auxp + col0 + q * 4;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int64_t row = row0 + (lane >> 3) + 4 * i;
-    if (col_ok && row < M)
+    if (col_ok && row < M) {
+      const int64_t arow = aux_rows ? __ldg(aux_rows + row) : row;        // gathered target: the row of the dataset this batch row came from
       asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(ax.v[i].x), "=f"(ax.v[i].y), "=f"(ax.v[i].z), "=f"(ax.v[i].w) : "l"(sp + row * ldaux));
-    else ax.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                   : "=f"(ax.v[i].x), "=f"(ax.v[i].y), "=f"(ax.v[i].z), "=f"(ax.v[i].w) : "l"(sp + arow * ldaux));
+    } else ax.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 __device__ __forceinline__ float4 rt_lds128(uint32_t a) {
@@ -454,7 +456,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NOISE ? TC2_THREADS_
         const bool row_valid = row < p.M;
         const int64_t ncol0 = (int64_t)nb * TC2_BN;
         RtAux ax;
-        rt_load_aux(auxp, ldaux, row0, p.M, ncol0 + half * 32, p.N, lane, ax);
+        const int64_t* arows = (p.ep.mode == EPI_LOSS_TRAIN || p.ep.mode == EPI_LOSS_PRED) ? p.ep.aux_rows : nullptr;
+        rt_load_aux(auxp, ldaux, row0, p.M, ncol0 + half * 32, p.N, lane, ax, arows);
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
 #pragma unroll 1
@@ -468,7 +471,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NOISE ? TC2_THREADS_
           if (auxp) rt_stage_aux(tile_s, lane, ax);
           float* cs_row = p.ep.colsum_partials ? p.ep.colsum_partials + (row0 >> 5) * p.N : nullptr;
           rt_dispatch(p.ep, r, ax, col0, p.N, row + p.ep.row0, row_valid, tile_s, lane, loss_acc, cs_row);
-          if (ch + 2 < TC2_BN / 32) rt_load_aux(auxp, ldaux, row0, p.M, col0 + 64, p.N, lane, ax);   // next chunk's aux, behind this chunk's store
+          if (ch + 2 < TC2_BN / 32) rt_load_aux(auxp, ldaux, row0, p.M, col0 + 64, p.N, lane, ax, arows);   // next chunk's aux, behind this chunk's store
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) { rt_tma_store(&p.tmC, tile_s, (int)col0, (int)row0); asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -479,3 +479,22 @@ def test_modality_rmse_batched_pass():
     want = O.reconstruction_loss_per_modality(ocfg, P, X.astype(np.float32).astype(np.float64))
     assert np.allclose(got, want, rtol=1e-5)
     e.close()
+
+
+def test_resident_step_gathers_the_loss_target_of_wide_models():
+    """Wide models: the resident-dataset step writes no clean copy of the batch; the loss GEMM's row-layout epilogue reads the
+    target rows of the dataset through the sampled index list.  Same result, bit for bit, as the step fed the gathered batch."""
+    ocfg, ecfg = make_cfgs(num_feats=1024, starts=[0, 256, 512, 640, 768, 1024], layers=(384, 64), tie=False, precision='tf32')
+    rng, X = _data(ocfg, 2000, 13)
+    P = O.init_params(ocfg, rng)
+    a, b = _engine(ecfg, P), _engine(ecfg, P)
+    a.set_dataset(0, X)
+    for step in (5, 6):
+        a.set_rng_step(step); b.set_rng_step(step)
+        a.train_step_resident(0, 512, idx=None, gen_noise=True)
+        idx = PH.batch_indices(0, step, 512, 2000)
+        b.train_step(X[idx].astype(np.float32), noise='gen')
+        assert a.scalars()['recon_loss'] == b.scalars()['recon_loss']
+    for k in P:
+        assert np.array_equal(a.get_variable(k), b.get_variable(k)), k
+    a.close(); b.close()
