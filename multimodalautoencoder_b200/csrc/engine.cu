@@ -530,6 +530,17 @@ struct mmae_engine {
   // Small models: Adam rewrites the K-major weight shadows in the same pass (scattered 4-byte stores beat a launch);
   // the shadows are then always current outside a step, and captured graphs need no transpose launch.
   bool shadow_in_adam() const { return cfg.precision == MMAE_PREC_TF32 && nP <= ((int64_t)1 << 21); }
+  // ... large models get the same guarantee from the tiled Adam pass (adam_tiled_kernel) when every optimizer's variables
+  // fit its table: either way the shadows are current outside a step and captured graphs carry no transpose launch
+  bool adam_keeps_shadows() const {
+    if (cfg.precision != MMAE_PREC_TF32) return false;
+    if (shadow_in_adam()) return true;
+    static const bool tiled_off = getenv("MMAE_ADAM_TILED") && getenv("MMAE_ADAM_TILED")[0] == '0';
+    if (tiled_off) return false;
+    int n0 = 0, n1 = 0;
+    for (const Var& v : vars) { if (v.off < enc_end) ++n0; if (v.off >= enc_begin) ++n1; }
+    return n0 <= AdamTiles::kMax && (H == 0 || n1 <= AdamTiles::kMax);
+  }
   // Fast small-config train step (train_core only, no data parallelism): the loss partials of the forward chain are
   // summed, and the per-step scalars finalised, inside grad_assemble_kernel instead of in launches of their own.
   bool fast_step = false;
@@ -718,7 +729,7 @@ struct mmae_engine {
     }
     // capture.  All K-major weight shadows are forced stale so that the graph always refreshes the ones it reads.
     const size_t idx = (size_t)(ge - graphs.data());
-    if (!shadow_in_adam()) std::fill(pt_dirty.begin(), pt_dirty.end(), 1);
+    if (!adam_keeps_shadows()) std::fill(pt_dirty.begin(), pt_dirty.end(), 1);
     else { int rr = refresh_shadows(); if (rr) return rr; }     // (current outside steps: set_variable refreshes eagerly, Adam rewrites them)
     const int64_t l0 = launches, c0 = chain_launches, bc0 = bchain_launches, wg0 = wgroup_launches, cap0 = cap, capa0 = cap_acts, caph0 = cap_host, sk0 = splitk_cap;
     cudaGraph_t graph = nullptr;
@@ -1406,6 +1417,29 @@ struct mmae_engine {
     a.alpha = &d_state->alpha[opt];
     a.b1 = cfg.beta1; a.b2 = cfg.beta2; a.eps = cfg.adam_eps; a.scalars_out = d_scalars;
     a.PT = shadow_in_adam() ? PT : nullptr;
+    // large tf32 models: tiled pass that rewrites the K-major shadows too (no transpose launches at the next forward)
+    static const bool tiled_off = getenv("MMAE_ADAM_TILED") && getenv("MMAE_ADAM_TILED")[0] == '0';
+    if (!a.PT && !tiled_off && cfg.precision == MMAE_PREC_TF32) {
+      AdamTiles g; g.n = 0; int tiles = 0; bool fits = true;
+      for (size_t i = 0; i < vars.size(); ++i) {
+        Var& v = vars[i];
+        if (v.off < b || v.off >= e) continue;
+        if (g.n == AdamTiles::kMax) { fits = false; break; }
+        const int rows = v.cols > 0 ? (int)v.rows : 1, cols = v.cols > 0 ? (int)v.cols : (int)v.rows;
+        g.off[g.n] = v.off; g.rows[g.n] = rows; g.cols[g.n] = cols; g.l2[g.n] = v.l2[opt]; g.shadow[g.n] = v.cols > 0 ? 1 : 0;
+        g.tile0[g.n] = tiles; tiles += ((rows + 31) / 32) * ((cols + 31) / 32);
+        ++g.n;
+      }
+      if (fits && g.n > 0) {
+        g.tile0[g.n] = tiles;
+        a.PT = PT;
+        adam_tiled_kernel<<<tiles, dim3(32, 8), 0, st>>>(a, g);
+        CKL("adam_tiled");
+        for (size_t i = 0; i < vars.size(); ++i) if (vars[i].off >= b && vars[i].off < e) pt_dirty[i] = 0;
+        return 0;
+      }
+      a.PT = nullptr;
+    }
     adam_kernel<<<grid_for(e - b, 256), 256, 0, st>>>(a);
     CKL("adam");
     for (size_t i = 0; i < vars.size(); ++i) {
@@ -1643,7 +1677,7 @@ int mmae_set_variable(mmae_engine* e, const char* name, const float* host, int64
   if (r == 0) {
     Var* v = e->find(name);
     e->mark_dirty(v->off, v->off + 1);
-    if (e->shadow_in_adam() && v->cols > 0) r = e->refresh_shadows();      // keep "shadows are current outside a step" true
+    if (e->adam_keeps_shadows() && v->cols > 0) r = e->refresh_shadows();      // keep "shadows are current outside a step" true
   }
   return r;
 }

@@ -472,6 +472,56 @@ __global__ void grad_sqnorm_kernel(const float* __restrict__ P, const float* __r
   }
 }
 
+// Large models: Adam over 32 x 32 tiles of every variable of the range, so that the K-major shadow of a weight matrix
+// (what the tcgen05 forward GEMMs read) is rewritten through shared memory in the same pass -- coalesced both ways -- instead
+// of by transpose launches at the top of the next forward.  Vectors ride along as [1, n] matrices (no shadow).
+struct AdamTiles {
+  static constexpr int kMax = 24;
+  int n;
+  int64_t off[kMax]; int rows[kMax], cols[kMax]; float l2[kMax]; int shadow[kMax];
+  int tile0[kMax + 1];
+};
+__global__ void __launch_bounds__(256) adam_tiled_kernel(const AdamArgs a, const AdamTiles g) {
+  __shared__ float t[32][33];
+  float scale = 1.f;
+  if (a.scale_mode == 1) scale = (float)(1.0 / sqrt(a.n_elems * a.sums[0]));
+  float clip = 1.f;
+  if (a.scale_mode == 2) { const double nrm = sqrt(a.sums[6]); clip = (float)((double)a.clip_norm / fmax(nrm, (double)a.clip_norm)); }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && a.scalars_out) a.scalars_out[MMAE_S_GRAD_SCALE] = scale;
+  const float alpha = __ldg(a.alpha);
+  int v = 0;
+  while (v + 1 < g.n && (int)blockIdx.x >= g.tile0[v + 1]) ++v;
+  const int rows = g.rows[v], cols = g.cols[v];
+  const int tiles_c = (cols + 31) / 32;
+  const int tl = blockIdx.x - g.tile0[v];
+  const int c0 = (tl % tiles_c) * 32, r0 = (tl / tiles_c) * 32;
+  const int64_t off = g.off[v];
+  const float l2 = g.l2[v];
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float pn = 0.f;
+    if (r < rows && c < cols) {
+      const int64_t gi = off + (int64_t)r * cols + c;
+      const int64_t k = gi - a.begin;
+      const float p = a.P[gi];
+      const float gr = (scale * a.G[gi] + l2 * p) * clip;
+      float m = a.M[k], vv = a.V[k];
+      m += (gr - m) * (1.f - a.b1);
+      vv += (gr * gr - vv) * (1.f - a.b2);
+      a.M[k] = m; a.V[k] = vv;
+      pn = p - alpha * m / (sqrtf(vv) + a.eps);
+      a.P[gi] = pn;
+    }
+    t[i][threadIdx.x] = pn;
+  }
+  if (!g.shadow[v]) return;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) a.PT[off + (int64_t)c * rows + r] = t[threadIdx.x][i];
+  }
+}
+
 // Per-step state kept in DEVICE memory so that a captured CUDA graph of the train step replays unchanged: the Philox
 // step index every random draw is keyed by, and the two optimizers' step counts with their bias-corrected rates.
 struct StepState { uint32_t step; uint32_t pad; long long t[2]; float alpha[2]; };
