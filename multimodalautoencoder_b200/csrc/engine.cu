@@ -765,20 +765,21 @@ struct mmae_engine {
     static const bool want_trace = getenv("MMAE_CHAIN_TRACE") != nullptr;
     if (!want_trace) return nullptr;
     long long* trace = nullptr;
-    cudaMalloc(&trace, 64 * CH_MAX_OPS * 4 * 8); cudaMemsetAsync(trace, 0, 64 * CH_MAX_OPS * 4 * 8, stream); cp.trace = trace;
+    cudaMalloc(&trace, 2 * 64 * CH_MAX_OPS * 4 * 8); cudaMemsetAsync(trace, 0, 2 * 64 * CH_MAX_OPS * 4 * 8, stream); cp.trace = trace;
     return trace;
   }
   void trace_end(const ChainParams& cp, long long* trace, const char* tag) {
     if (!trace) return;
-    std::vector<long long> h(64 * CH_MAX_OPS * 4);
+    std::vector<long long> h(2 * 64 * CH_MAX_OPS * 4);
     cudaStreamSynchronize(stream);
     cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost); cudaFree(trace);
     const long long t0 = h[0];
     for (int it = 0; it < 8 && it * num_sms < cp.m_tiles; ++it)
       for (int i = 0; i < cp.nops; ++i) {
         const long long* q = &h[(it * CH_MAX_OPS + i) * 4];
-        fprintf(stderr, "[chain trace %s] tile %d op %d: mma start %8lld issued %8lld | epi start %8lld end %8lld\n", tag, it, i,
-                q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0);
+        const long long* w = &h[64 * CH_MAX_OPS * 4 + (it * CH_MAX_OPS + i) * 4];
+        fprintf(stderr, "[chain trace %s] tile %d op %d: mma start %8lld issued %8lld | epi start %8lld end %8lld | issuer waited: A-chunks %6lld W %6lld X %6lld\n",
+                tag, it, i, q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0, w[0], w[1], w[2]);
       }
   }
   int64_t chain_launches = 0;

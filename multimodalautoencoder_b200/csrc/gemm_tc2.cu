@@ -471,7 +471,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NOISE ? TC2_THREADS_
           if (auxp) rt_stage_aux(tile_s, lane, ax);
           float* cs_row = p.ep.colsum_partials ? p.ep.colsum_partials + (row0 >> 5) * p.N : nullptr;
           rt_dispatch(p.ep, r, ax, col0, p.N, row + p.ep.row0, row_valid, tile_s, lane, loss_acc, cs_row);
-          if (ch + 2 < TC2_BN / 32) rt_load_aux(auxp, ldaux, row0, p.M, col0 + 64, p.N, lane, ax, arows);   // next chunk's aux, behind this chunk's store
+          // next chunk's aux, behind this chunk's arithmetic.  (Measured and dropped: issuing these loads BEFORE the arithmetic
+          // into a second register set -- 168 registers with spills -- made the aux-carrying launches 1.3-2.2x slower.)
+          if (ch + 2 < TC2_BN / 32) rt_load_aux(auxp, ldaux, row0, p.M, col0 + 64, p.N, lane, ax, arows);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) { rt_tma_store(&p.tmC, tile_s, (int)col0, (int)row0); asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
