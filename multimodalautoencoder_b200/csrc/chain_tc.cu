@@ -489,13 +489,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
           if (i == last && it > 0) { mbar_wait_parked(last_done, par ^ 1); tc_fence_after(); }   // previous tile's result drained
           const uint32_t idesc = idesc_tf32_rt(TC_BM, n_chunk);
           const uint32_t cd_s = smem_u32(&chunk_done[(i > 0 ? i - 1 : 0) * CH_MAX_CHUNKS]);
+#ifdef MMAE_CHAIN_TRACE_WAITS
           const bool tracing = p.trace && blockIdx.x == 0 && it < 64;
           long long wait_a = 0, wait_w = 0, wait_x = 0;
           if (tracing) p.trace[(it * CH_MAX_OPS + i) * 4 + 0] = clock64();
+#else
+          if (p.trace && blockIdx.x == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 0] = clock64();
+#endif
           for (int nc = 0; nc < n_chunks; ++nc) {
             const uint32_t tmem_d = tmem_base + d_col + (uint32_t)(nc * n_chunk);
             uint32_t accumulate = 0;
             for (int k = 0; k < K; k += TC_BK) {
+#ifdef MMAE_CHAIN_TRACE_WAITS      // (compile-time: the single-lane issuer must stay lean, see the note above)
               if (tracing) {      // debug timeline: where the issuer waits (activated A chunk / weight chunk / X chunk)
                 const long long c0 = clock64();
                 if (a_tmem && nc == 0) mbar_wait_s(cd_s + (uint32_t)(k >> 5) * 8u, par);
@@ -505,7 +510,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
                 if (!a_tmem) mbar_wait_s(xfull_s + xs * 8u, xph);
                 const long long c3 = clock64();
                 wait_a += c1 - c0; wait_w += c2 - c1; wait_x += c3 - c2;
-              } else {
+              } else
+#endif
+              {
               if (a_tmem && nc == 0) mbar_wait_s(cd_s + (uint32_t)(k >> 5) * 8u, par);    // A columns [k, k+32) written
               mbar_wait_s(wfull_s + ws * 8u, wph);
               if (!a_tmem) mbar_wait_s(xfull_s + xs * 8u, xph);
@@ -534,11 +541,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
             }
           }
           tc_commit(&mma_done[i]);
+#ifdef MMAE_CHAIN_TRACE_WAITS
           if (tracing) {
             p.trace[(it * CH_MAX_OPS + i) * 4 + 1] = clock64();
             long long* w = p.trace + 64 * CH_MAX_OPS * 4 + (it * CH_MAX_OPS + i) * 4;
             w[0] = wait_a; w[1] = wait_w; w[2] = wait_x;
           }
+#else
+          if (p.trace && blockIdx.x == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 1] = clock64();
+#endif
         }
       }
     }
