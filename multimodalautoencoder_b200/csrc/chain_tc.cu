@@ -746,7 +746,7 @@ cudaError_t chain_launch(const ChainParams& p, int grid, cudaStream_t st) {
   static bool configured_dev[64] = {};        // the attribute is per device: one flag per device ordinal
   int dev_ = 0; cudaGetDevice(&dev_);
   bool& configured = configured_dev[dev_ & 63];
-  if (!configured) {
+  if (!configured || dev_ >= 64) {      // (ordinals past the table are configured on every launch instead of aliasing)
     cudaError_t e = cudaFuncSetAttribute(chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
     if (e != cudaSuccess) return e;

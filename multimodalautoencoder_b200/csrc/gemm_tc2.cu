@@ -539,7 +539,7 @@ static cudaError_t tc2_launch_inst(const TcParams& p, int grid, cudaStream_t st)
   int dev_ = 0; cudaGetDevice(&dev_);
   bool& configured = configured_dev[dev_ & 63];
   auto kern = gemm_tc2_kernel<A_MN, B_MN, NOISE>;
-  if (!configured) {
+  if (!configured || dev_ >= 64) {      // (ordinals past the table are configured on every launch instead of aliasing)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM);
     if (e != cudaSuccess) return e;
     configured = true;

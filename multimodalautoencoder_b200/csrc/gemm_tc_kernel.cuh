@@ -413,7 +413,7 @@ inline cudaError_t tc_launch_inst(const TcParams& p, int grid, cudaStream_t st) 
   int dev_ = 0; cudaGetDevice(&dev_);
   bool& configured = configured_dev[dev_ & 63];
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
-  if (!configured) {
+  if (!configured || dev_ >= 64) {      // (ordinals past the table are configured on every launch instead of aliasing)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;

@@ -172,7 +172,7 @@ cudaError_t wgrad_group_launch(const WgParams& p, int grid, cudaStream_t st) {
   static bool configured_dev[64] = {};
   int dev_ = 0; cudaGetDevice(&dev_);
   bool& configured = configured_dev[dev_ & 63];
-  if (!configured) {
+  if (!configured || dev_ >= 64) {      // (ordinals past the table are configured on every launch instead of aliasing)
     cudaError_t e = cudaFuncSetAttribute(wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;

@@ -42,6 +42,11 @@ def test_tc_gemm(shape, ta, tb):
     torch.cuda.synchronize()
     rel = ((C.double() - ref).norm() / ref.norm()).item()
     assert rel < 1e-3, rel
+    # per element: every product carries two operand roundings of 2^-11 each, the K products add up like a random walk:
+    # |error| <= 6 sigma with sigma = 2^-11 * sqrt(2 K) for unit-variance operands (a misplaced tile or a dropped k-block
+    # shows up as an O(sqrt(K)) error in single elements long before it moves the Frobenius norm)
+    bound = 6.0 * 2.0 ** -11 * np.sqrt(2.0 * K) + 1e-6
+    assert (C.double() - ref).abs().max().item() <= bound, ((C.double() - ref).abs().max().item(), bound)
 
 
 def test_tc_gemm_bias_act_beta():
