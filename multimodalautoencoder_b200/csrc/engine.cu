@@ -1083,6 +1083,9 @@ struct mmae_engine {
   int backward_group(int64_t B) {
     static const bool group_off = getenv("MMAE_WGRAD_GROUP") && getenv("MMAE_WGRAD_GROUP")[0] == '0';
     if (group_off || dp_on() || x_noise.enabled) return 0;
+    if (nP > ((int64_t)1 << 21)) return 0;          // large models: their weight gradients fill the two-SM GEMM on their own
+    if (!dL_fused) return 0;                        // the assembly reads every bias gradient from fused per-32-row partials
+    for (char f : dch_fused) if (!f) return 0;
     const bool tied = cfg.tie_weights != 0;
     struct Item { WgDesc d; Var* v; };
     std::vector<Item> items;
@@ -1269,9 +1272,13 @@ struct mmae_engine {
     { int cr = backward_chain(B, keep); if (cr < 0) return cr;
       if (cr == 1) { dch_fused.assign(2 * L - 1, 1); dL_fused = true; return backward_recon_from_chain(B); } }
     static const bool reorder_off = getenv("MMAE_DP_REORDER") && getenv("MMAE_DP_REORDER")[0] == '0';
-    if (dp_on() && !reorder_off && !cfg.variational && L >= 2) {
+    // Per-layer dgrads first, each delta in its own buffer; then the weight gradients: bucket-size order under data
+    // parallelism, the grouped launch + one assembly launch for small models whose chain does not fit TMEM (e.g. the
+    // classification config [200, 100]: 12 launches per reconstruction step instead of 27).
+    const bool small_tc = cfg.precision == MMAE_PREC_TF32 && B >= 32 && nP <= ((int64_t)1 << 21);
+    if ((dp_on() || small_tc) && !reorder_off && !cfg.variational && L >= 2) {
       RET(backward_dgrads_layerwise(B, keep));
-      return backward_recon_from_chain(B, true);
+      return backward_recon_from_chain(B, dp_on());
     }
     float* d = out; int64_t ldd = F;       // delta_L from the EPI_LOSS_TRAIN epilogue
     float* nxt = dA;
