@@ -176,23 +176,40 @@ __device__ __forceinline__ void chain_act_dispatch(const ChainOp& o, const CUten
 // v = (delta . W^T) * act'(h) * dropmask/keep with h the saved forward activation; TMEM <- tf32(v)
 // in place (the next dgrad op's A operand), global copy of delta for the weight-gradient GEMMs through the swizzled
 // tile + TMA store, per-32-row column sums (bias gradient) read back column-wise from the same tile.
-// The saved activations are read straight from global memory (thread = row, 8 x 16 B): the loads are issued before the
-// accumulator is awaited, so their latency hides behind the MMAs of this op.
+// The saved activations are read with COALESCED 16-byte global loads (load i of lane l covers row 4i + l/8, columns
+// 4 (l%8) .. +3 of the chunk: four full 128-byte row segments per instruction), issued before the accumulator is awaited so
+// that their latency hides behind the MMAs of this op, and reach the row-per-thread layout through the warp's swizzled
+// staging tile.  (First version: one row per thread, 8 x 16 B -- every instruction touched 32 lines; the op-0 epilogue then
+// took 15-17 K clocks per tile, see profiles/r02_chain_trace_small_train.txt.)
 struct DgradAux { float4 v[8]; };
-__device__ __forceinline__ void chain_dgrad_load_aux(const ChainOp& o, int col0, int64_t row, int64_t M, DgradAux& ax) {
-  const bool row_ok = row < M && o.ep.saved != nullptr;
-  const float* sp = o.ep.saved + row * o.ep.lds + col0;
+__device__ __forceinline__ void chain_dgrad_load_aux(const ChainOp& o, int col0, int64_t row0, int64_t M, int lane, DgradAux& ax) {
+  const int q = lane & 7;
+  const bool col_ok = o.ep.saved != nullptr && (col0 + q * 4 + 3 < o.N);
+  const float* sp = o.ep.saved + col0 + q * 4;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const bool ok = row_ok && (col0 + q * 4 + 3 < o.N);
-    if (ok) asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(ax.v[q].x), "=f"(ax.v[q].y), "=f"(ax.v[q].z), "=f"(ax.v[q].w) : "l"(sp + q * 4));
-    else ax.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < 8; ++i) {
+    const int64_t row = row0 + (lane >> 3) + 4 * i;
+    if (col_ok && row < M) asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                        : "=f"(ax.v[i].x), "=f"(ax.v[i].y), "=f"(ax.v[i].z), "=f"(ax.v[i].w) : "l"(sp + row * o.ep.lds));
+    else ax.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+// column sums over the 32 rows (lanes) of a chunk held one row per lane: transposing butterfly, 31 shuffles, fixed tree
+__device__ __forceinline__ float chain_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { const bool up = lane & 16; const float send = up ? v[j] : v[j + 16]; const float keep = up ? v[j + 16] : v[j]; v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const bool up = lane & 8; const float send = up ? v[j] : v[j + 8]; const float keep = up ? v[j + 8] : v[j]; v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const bool up = lane & 4; const float send = up ? v[j] : v[j + 4]; const float keep = up ? v[j + 4] : v[j]; v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) { const bool up = lane & 2; const float send = up ? v[j] : v[j + 2]; const float keep = up ? v[j + 2] : v[j]; v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2); }
+  { const bool up = lane & 1; const float send = up ? v[0] : v[1]; const float keep = up ? v[1] : v[0]; v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1); }
+  return v[0];
 }
 template <int ACT, bool DROP>
 __device__ __forceinline__ void chain_dgrad_chunk(const ChainOp& o, const CUtensorMap* tmO, uint32_t taddr, int col0, int64_t tile_row0,
-                                                  int64_t M, int quad, int lane, const DgradAux& ax, EpiStage& es) {
+                                                  int64_t M, int quad, int lane, DgradAux& ax, EpiStage& es) {
   uint32_t r[32];
   tc_ld32(taddr, r);
   const uint32_t tile = smem_u32(es.buf[0]);
@@ -200,12 +217,19 @@ __device__ __forceinline__ void chain_dgrad_chunk(const ChainOp& o, const CUtens
     if (lane == 0) bulk_wait_read<0>();
     __syncwarp();
   }
+  const bool staged = o.ep.saved && o.has_out;
+  if (staged) {        // coalesced-load layout -> row layout through the staging tile; each thread then reads its own row chunk by chunk
+    const int q = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int rr = (lane >> 3) + 4 * i; sts128(tile + rr * 128 + ((q ^ (rr & 7)) << 4), ax.v[i]); }
+    __syncwarp();
+  }
   const int64_t lrow = tile_row0 + quad * 32 + lane;
   const int64_t grow = lrow + o.ep.row0;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float hs[4] = {ax.v[q].x, ax.v[q].y, ax.v[q].z, ax.v[q].w};
-    float v[4];
+    const float4 h4 = staged ? lds128(row_chunk(tile, lane, q)) : make_float4(0.f, 0.f, 0.f, 0.f);      // (read before this chunk's result overwrites it)
+    const float hs[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float g = __uint_as_float(r[q * 4 + e]);
@@ -214,24 +238,20 @@ __device__ __forceinline__ void chain_dgrad_chunk(const ChainOp& o, const CUtens
         uint32_t w = philox_word((uint64_t)grow * (uint64_t)o.ep.drop_width + (uint64_t)(col0 + q * 4 + e), o.ep.drop_stream, __ldg(o.ep.step), o.ep.seed);
         if ((w >> 8) < o.ep.keep_thr) { g = g / o.ep.keep; h = h * o.ep.keep; } else { g = 0.f; }
       }
-      v[e] = g * dact_t<ACT>(h);
-      r[q * 4 + e] = to_tf32(v[e]);
+      r[q * 4 + e] = __float_as_uint(g * dact_t<ACT>(h));
     }
-    if (o.has_out) sts128(row_chunk(tile, lane, q), make_float4(v[0], v[1], v[2], v[3]));
+    if (o.has_out) sts128(row_chunk(tile, lane, q), make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                                                                __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3])));
   }
+  float outv[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { outv[j] = __uint_as_float(r[j]); r[j] = to_tf32(outv[j]); }
   tc_st32(taddr, r);
   if (o.has_out) {
-    __syncwarp();
-    if (o.ep.colsum_partials) {
-      const int col = col0 + lane;
+    if (o.ep.colsum_partials) {          // rows past M hold exact zeros (zero-filled operands, zero aux)
       const int64_t row0 = tile_row0 + quad * 32;
-      if (row0 < M) {
-        float cs = 0.f;
-#pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr)        // rows past M hold exact zeros (zero-filled operands, zero aux)
-          cs += lds32(tile + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4);
-        if (col < o.N) o.ep.colsum_partials[(row0 >> 5) * o.N + col] = cs;
-      }
+      const float cs = chain_colsum32(outv, lane);
+      if (row0 < M && col0 + lane < o.N) o.ep.colsum_partials[(row0 >> 5) * o.N + col0 + lane] = cs;
     }
     fence_async_smem();
     __syncwarp();
@@ -241,7 +261,7 @@ __device__ __forceinline__ void chain_dgrad_chunk(const ChainOp& o, const CUtens
 }
 template <bool DROP>
 __device__ __forceinline__ void chain_dgrad_dispatch(const ChainOp& o, const CUtensorMap* tmO, uint32_t taddr, int col0, int64_t tile_row0,
-                                                     int64_t M, int quad, int lane, const DgradAux& ax, EpiStage& es) {
+                                                     int64_t M, int quad, int lane, DgradAux& ax, EpiStage& es) {
   switch (o.ep.act) {
     case MMAE_ACT_RELU: chain_dgrad_chunk<MMAE_ACT_RELU, DROP>(o, tmO, taddr, col0, tile_row0, M, quad, lane, ax, es); break;
     case MMAE_ACT_TANH: chain_dgrad_chunk<MMAE_ACT_TANH, DROP>(o, tmO, taddr, col0, tile_row0, M, quad, lane, ax, es); break;
@@ -610,7 +630,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
       for (int i = 0; i < last; ++i) {
         const ChainOp& o = p.op[i];
         DgradAux dax;
-        if (BWD && half < o.n_chunk / 32) chain_dgrad_load_aux(o, half * 32, tile_row0 + quad * 32 + lane, p.M, dax);
+        if (BWD && half < o.n_chunk / 32) chain_dgrad_load_aux(o, half * 32, tile_row0 + quad * 32, p.M, lane, dax);
         mbar_wait_parked(&mma_done[i], par);
         tc_fence_after();
         if (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64) p.trace[(it * CH_MAX_OPS + i) * 4 + 2] = clock64();
@@ -618,7 +638,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
         const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)o.d_col;
         for (int ch = half; ch < chunks; ch += 2) {
           if (BWD) {
-            if (ch != half) chain_dgrad_load_aux(o, ch * 32, tile_row0 + quad * 32 + lane, p.M, dax);     // (the first chunk's loads were issued before the wait)
+            if (ch != half) chain_dgrad_load_aux(o, ch * 32, tile_row0 + quad * 32, p.M, lane, dax);     // (the first chunk's loads were issued before the wait)
             if (o.ep.keep < 1.f) chain_dgrad_dispatch<true>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, p.M, quad, lane, dax, es);
             else chain_dgrad_dispatch<false>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, p.M, quad, lane, dax, es);
           } else if (o.ep.keep < 1.f) chain_act_dispatch<true>(o, &p.tmO[i], tbase + ch * 32, ch * 32, tile_row0, quad, lane, smem_u32(bias_s + o.bias_off), es);

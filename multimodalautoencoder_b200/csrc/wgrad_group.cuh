@@ -40,8 +40,6 @@ struct WgParams {
 struct WgDesc {
   const float* A; int64_t lda; int M;      // in  [batch, M]
   const float* B; int64_t ldb; int N;      // delta [batch, N]
-  int var;                                 // index of the variable the result is summed into
-  int transposed_out;                      // unused (both orientations are expressed by swapping A and B)
 };
 
 struct WgPlan { int splits; int64_t k_per_split; int grid; int tiles; };
