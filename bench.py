@@ -152,6 +152,38 @@ def cpu_port_run(name, steps, warmup, sample_rows):
                        % (steps, sample_rows, name, w['B'], what))
 
 
+def reference_code_run(name, rows, steps=2):
+    """The reference's OWN train loop (oracle/_ref: its multimodal_autoencoder.py converted to py3, on the TF-1 API shim in
+    fp32 over torch's CPU kernels) on a small bounded sample.  Reported beside the port so that the choice of baseline is
+    visible: the port is the faster CPU implementation of the two and is therefore the one used as the baseline."""
+    import contextlib
+    import io
+    import numpy as np
+    import torch
+    from oracle.ref_loader import load_reference
+    ref = load_reference(torch.float32)
+    if ref is None:
+        return None
+    w, starts, names = workload_cfg(name)
+    torch.set_num_threads(os.cpu_count() or 1)
+    rng = np.random.default_rng(0)
+    X = rng.uniform(0, 1, (rows, w['F']))
+    dl = ref.make_loader(X, X[:200], starts, names)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ref.mmae.MultimodalAutoencoder(data_loader=dl, layer_sizes=list(w['layers']), variational=False, tie_weights=w['tie'],
+                                           batch_size=rows, learning_rate=1e-3, activation_func=w['act'], loss_func=w['loss'],
+                                           weight_initialization='normal', verbose=False)
+        np.random.seed(0)
+        m.train(1, record_every_nth=10 ** 9, save_every_nth=10 ** 9)
+        t0 = time.perf_counter()
+        m.train(steps, record_every_nth=10 ** 9, save_every_nth=10 ** 9)
+        dt = time.perf_counter() - t0
+    ref.tf.set_default_dtype(torch.float64)
+    return {'value': rows * steps / dt, 'unit': 'samples/s',
+            'sample': "%d steps x %d rows through the reference's own MultimodalAutoencoder.train() (one record step inside, :572-575)" % (steps, rows),
+            'note': 'reference Python (py3-converted) on the TF-1 API shim, fp32 torch CPU kernels; TensorFlow itself is not installable here'}
+
+
 METRIC = {'wide': 'MMAE train samples/sec (fwd+bwd+Adam)', 'small': 'MMAE train samples/sec (fwd+bwd+Adam)',
           'cls': 'MMAE train samples/sec (fwd+bwd+Adam), reconstruction step + classification-head step',
           'infer': 'MMAE fill-in inference samples/sec (reconstruction forward + missing-block fill)'}
@@ -177,6 +209,12 @@ def run_reference(args):
     while rows > 256 and per_row * rows * (args.steps + max(args.warmup, 1)) > CPU_BUDGET_S:
         rows //= 2
     r = cpu_port_run(name, args.steps, max(args.warmup, 1), rows)
+    own = None
+    if name in ('wide', 'small'):
+        try:
+            own = reference_code_run(name, 1024 if name == 'wide' else 8192)
+        except Exception as e:      # noqa: BLE001 -- an extra, never the line itself
+            own = {'error': repr(e)[:200]}
     line = {
         'impl': 'reference', 'metric': METRIC[name], 'value': r['value'], 'unit': 'samples/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * r['seconds'] / args.steps,
@@ -186,7 +224,7 @@ def run_reference(args):
                    'rows_per_step': rows, 'same_rows_as_gpu_arm': rows == w['B'],
                    'note': 'CPU port of the reference step on all host cores (the TensorFlow-1.x reference cannot run here)'},
         'cpu_baseline': {'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
-                         'noise_loop_share': r['noise_share']},
+                         'noise_loop_share': r['noise_share'], 'reference_code_via_shim': own},
         'e2e': {'value': r['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
