@@ -141,3 +141,37 @@ def test_wide_synthetic_shape():
     blocks = wide_blocks()
     assert len(blocks) == 16 and sum(w for _, w in blocks) == 4096
     assert {'call', 'sms', 'screen', 'location'} <= {n for n, _ in blocks}
+
+
+def test_svm_scoring_uses_one_embedding_pass(tmp_path):
+    """MMAEWrapper.test_embedding_classification_quality: the four row sets (train / val / clean val / noisy val) are
+    embedded in ONE session.run and split back in order (the reference ran four, autoencoder_wrapper.py:212-226)."""
+    from multimodalautoencoder_b200.autoencoder_wrapper import MMAEWrapper
+    dl, cdl = _fake_loaders()
+    w = MMAEWrapper('synthetic.csv', dropbox_path=str(tmp_path) + '/', data_loader=dl, classification_data_loader=cdl)
+    calls = []
+
+    class FakeSession:
+        def run(self, fetch, feed):
+            X = feed['noisy_X']
+            calls.append(len(X))
+            return np.asarray(X)[:, :6] * 2.0                     # a row-wise "embedding"
+
+    class FakeModel:
+        val_loss = [1.0]
+        embedding, noisy_X, tf_dropout_prob = 'embedding', 'noisy_X', 'keep'
+        session = FakeSession()
+
+    w.model = FakeModel()
+    seen = {}
+    orig = w.svm_pred_best_result
+
+    def spy(svm_model, X, Y, label, best_acc, best_auc):
+        seen[len(X)] = X
+        return orig(svm_model, X, Y, label, best_acc, best_auc)
+    w.svm_pred_best_result = spy
+    res = w.test_embedding_classification_quality()
+    assert len(calls) == 1 and calls[0] == len(cdl.train_X) + len(cdl.val_X) + len(cdl.clean_val_X) + len(cdl.noisy_val_X)
+    assert len(res) == 6 and all(r.shape == (1, 3) for r in res)
+    for part in (cdl.val_X, cdl.noisy_val_X, cdl.clean_val_X):     # each SVM sees exactly its own rows' embeddings
+        assert np.allclose(seen[len(part)], np.asarray(part)[:, :6] * 2.0)
