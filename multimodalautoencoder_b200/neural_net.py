@@ -220,3 +220,169 @@ class NeuralNetwork:
         if self.engine is not None:
             self.engine.close()
             self.engine = None
+
+
+DEFAULT_NUM_CROSS_FOLDS = 5
+LABELS_TO_PREDICT = ['happiness', 'health', 'calmness']
+
+
+def _wrapper_base():
+    from .generic_wrapper import ClassificationWrapper
+    return ClassificationWrapper
+
+
+class NNWrapper(_wrapper_base()):
+    """Grid search over the MLP's hyper-parameters (comparison_algorithms/neural_net.py:407-631): architecture x
+    dropout_prob x weight_penalty x learning_rate x batch_size, every setting trained on each cross-validation fold
+    with a fresh `NeuralNetwork`, metrics per label written into the results row.
+
+    Differences from the reference, both deliberate: the engine of the previous setting is destroyed before the next
+    one is built (the reference leaks a TF graph per setting), and `test_on_test` evaluates on the TEST rows -- the
+    reference passes `predict_on='test'`, which its own `train_and_predict` (:466-469, compares with 'Test') sends to
+    the validation rows and then scores against `test_Y`.
+    """
+
+    def __init__(self, filename, layer_sizes=[[300, 200, 100], [200, 100], [128, 64], [200, 100, 50]],
+                 dropout_probs=[0.5, 1.0], weight_penalties=[0.0, .01, .001, .0001], learning_rates=[.001],
+                 batch_sizes=[100], num_steps=5000, output_every_nth=5001, cont=False, classifier_name='NN',
+                 num_cross_folds=DEFAULT_NUM_CROSS_FOLDS, dropbox_path=DEFAULT_MAIN_DIRECTORY,
+                 datasets_path='Data/Cleaned/', results_path=None, check_test=True, normalize_and_fill=False,
+                 normalization='between_0_and_1', optimize_for='val_acc', min_or_max='max', save_results_every_nth=1,
+                 check_noisy_data=True, cross_validation=True, shard=None, *, data_loader=None, precision='tf32', seed=0,
+                 device=None):
+        self._given_loader = data_loader
+        self.layer_sizes = layer_sizes
+        self.dropout_probs = dropout_probs
+        self.weight_penalties = weight_penalties
+        self.batch_sizes = batch_sizes
+        self.learning_rates = learning_rates
+        self.num_steps = num_steps
+        self.output_every_nth = output_every_nth
+        self.precision, self.seed, self._device = precision, seed, device
+        self.model = None
+        _wrapper_base().__init__(
+            self, filename=filename, wanted_label=None, cont=cont, classifier_name=classifier_name,
+            num_cross_folds=num_cross_folds, dropbox_path=dropbox_path, datasets_path=datasets_path,
+            results_path=results_path, check_test=check_test, normalize_and_fill=normalize_and_fill,
+            normalization=normalization, optimize_for=optimize_for, min_or_max=min_or_max,
+            save_results_every_nth=save_results_every_nth, check_noisy_data=check_noisy_data,
+            cross_validation=cross_validation, shard=shard)
+
+    def load_data(self):
+        if self._given_loader is not None:           # a loader built by the caller (tests, in-memory frames)
+            self.data_loader = self._given_loader
+        else:
+            _wrapper_base().load_data(self)
+
+    def define_params(self):
+        self.params = {'architecture': self.layer_sizes, 'dropout_prob': self.dropout_probs,
+                       'weight_penalty': self.weight_penalties, 'learning_rate': self.learning_rates,
+                       'batch_size': self.batch_sizes}
+
+    def predict_on_data(self, X):
+        return self.model.predict(X)
+
+    def make_model(self, param_dict):
+        """One `NeuralNetwork` per (setting, fold); the previous engine goes first."""
+        if self.model is not None:
+            self.model.close()
+        self.model = NeuralNetwork(layer_sizes=param_dict['architecture'], batch_size=int(param_dict['batch_size']),
+                                   learning_rate=param_dict['learning_rate'], dropout_prob=param_dict['dropout_prob'],
+                                   weight_penalty=param_dict['weight_penalty'], data_loader=self.data_loader,
+                                   checkpoint_dir=None, verbose=False, precision=self.precision, seed=self.seed,
+                                   device=self._device)
+        return self.model
+
+    def train_and_predict(self, param_dict, predict_on='Val'):
+        predict_X = self.data_loader.test_X if predict_on == 'Test' else self.data_loader.val_X
+        self.make_model(param_dict)
+        self.model.train(num_steps=self.num_steps, output_every_nth=self.output_every_nth)
+        if predict_on == 'df':
+            return self.get_classification_predictions_from_df()
+        return self.predict_on_data(predict_X)
+
+    def test_on_test(self, param_dict):
+        return self.train_and_predict(param_dict, predict_on='Test')
+
+    @staticmethod
+    def _metrics(preds, true_y):
+        """[num_labels, 5] rows of (acc, auc, f1, precision, recall)."""
+        from .generic_wrapper import compute_all_classification_metrics
+        preds, true_y = np.asarray(preds), np.asarray(true_y)
+        if preds.ndim == 1:
+            preds, true_y = preds[:, None], true_y.reshape(len(true_y), -1)
+        return np.array([compute_all_classification_metrics(preds[:, l], true_y[:, l])
+                         for l in range(preds.shape[1])], dtype=np.float64)
+
+    def get_cross_validation_results(self, param_dict):
+        """Per-fold metrics for every label (:503-580); result columns keep the reference's names."""
+        dl = self.data_loader
+        n_labels = len(dl.wanted_labels)
+        all_m = np.full((self.num_cross_folds, n_labels, 5), np.nan)
+        noisy_m = np.full((self.num_cross_folds, n_labels, 5), np.nan)
+        clean_m = np.full((self.num_cross_folds, n_labels, 5), np.nan)
+        for f in range(self.num_cross_folds):
+            dl.set_to_cross_validation_fold(f)
+            preds = self.train_and_predict(param_dict)
+            all_m[f] = self._metrics(preds, dl.val_Y)
+            if self.check_noisy_data:
+                noisy_m[f] = self._metrics(self.predict_on_data(dl.noisy_val_X), dl.noisy_val_Y)
+                clean_m[f] = self._metrics(self.predict_on_data(dl.clean_val_X), dl.clean_val_Y)
+        for j, k in enumerate(('acc', 'auc', 'f1', 'precision', 'recall')):
+            param_dict['val_' + k] = np.nanmean(all_m[:, :, j])
+        print("Finished training all folds, average acc was", param_dict['val_acc'])
+        labels = LABELS_TO_PREDICT[:n_labels]
+        for i, label in enumerate(labels):
+            param_dict['val_acc_' + label] = np.nanmean(all_m[:, i, 0])
+            param_dict['val_auc_' + label] = np.nanmean(all_m[:, i, 1])
+        if self.check_noisy_data:
+            param_dict['noisy_val_acc'] = np.nanmean(noisy_m[:, :, 0])
+            param_dict['noisy_val_auc'] = np.nanmean(noisy_m[:, :, 1])
+            param_dict['clean_val_acc'] = np.nanmean(clean_m[:, :, 0])
+            param_dict['clean_val_auc'] = np.nanmean(clean_m[:, :, 1])
+            for i, label in enumerate(labels):
+                param_dict['noisy_val_acc_' + label] = np.nanmean(noisy_m[:, i, 0])
+                param_dict['noisy_val_auc_' + label] = np.nanmean(noisy_m[:, i, 1])
+                param_dict['clean_val_acc_' + label] = np.nanmean(clean_m[:, i, 0])
+                param_dict['clean_val_auc_' + label] = np.nanmean(clean_m[:, i, 1])
+        return param_dict
+
+    def get_final_results(self):
+        """Best setting by `optimize_for`, retrained and scored on the held-out test rows (:582-631). Returns the
+        [num_labels, 5] test metrics (None when check_test is off)."""
+        best_setting = self.find_best_setting()
+        print("\nThe best", self.optimize_for, "was", best_setting[self.optimize_for])
+        print("It was found with the following settings:")
+        print(best_setting)
+        if not self.check_test:
+            print("check_test is set to false, Will not evaluate performance on held-out test set.")
+            return None
+        dl = self.data_loader
+        preds = self.test_on_test(self.convert_param_dict_for_use(dict(best_setting)))
+        m = self._metrics(preds, dl.test_Y)
+        names = ('Acc:', 'AUC:', 'F1:', 'Precision:', 'Recall:')
+        noisy = clean = None
+        if self.check_noisy_data:
+            noisy = self._metrics(self.predict_on_data(dl.noisy_test_X), dl.noisy_test_Y)
+            clean = self._metrics(self.predict_on_data(dl.clean_test_X), dl.clean_test_Y)
+        for i, label in enumerate(LABELS_TO_PREDICT[:len(m)]):
+            print("\nFINAL TEST RESULTS ON ALL", label, "DATA:")
+            print(*[x for pair in zip(names, m[i]) for x in pair])
+            if noisy is not None:
+                print("FINAL TEST RESULTS ON NOISY", label, "DATA:")
+                print(*[x for pair in zip(names, noisy[i]) for x in pair])
+                print("FINAL TEST RESULTS ON CLEAN", label, "DATA:")
+                print(*[x for pair in zip(names, clean[i]) for x in pair])
+        print("Overall:", 'Acc:', np.mean(m[:, 0]), 'AUC:', np.mean(m[:, 1]))
+        return m
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) < 2:
+        print("usage: python -m multimodalautoencoder_b200.neural_net <filename> [<continue>] [<main dir>]")
+        sys.exit()
+    wrapper = NNWrapper(sys.argv[1], cont=len(sys.argv) >= 3 and sys.argv[2] == 'True',
+                        dropbox_path=sys.argv[3] if len(sys.argv) >= 4 else DEFAULT_MAIN_DIRECTORY)
+    print("\nThe validation results dataframe will be saved in:", wrapper.results_path + wrapper.save_prefix + '.csv')
+    wrapper.run()

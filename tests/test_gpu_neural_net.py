@@ -85,3 +85,37 @@ def test_train_protocol_matches_reference():
     assert preds.shape == rp.shape and np.mean(preds == rp) > 0.99
     assert 0.0 <= ours.test_on_validation() <= 1.0
     ours.close()
+
+
+def test_nn_wrapper_sweep_runs_the_engine(tmp_path):
+    """NNWrapper (comparison_algorithms/neural_net.py:407-631) on the engine: a 2-setting, 2-fold sweep writes one row per
+    setting with the reference's columns; what a fold trains is exactly a stand-alone NeuralNetwork with the same
+    hyper-parameters on that fold (same np.random stream -> identical predictions); the previous engine is destroyed."""
+    from multimodalautoencoder_b200.data_funcs import DataLoader
+    from multimodalautoencoder_b200.neural_net import NeuralNetwork, NNWrapper
+    from multimodalautoencoder_b200.synthetic import make_frame
+    df = make_frame(600, seed=8)
+    dl = DataLoader(df=df, supervised=True, cross_validation=True, normalize_and_fill=False, suppress_output=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        w = NNWrapper('synthetic.csv', layer_sizes=[[32, 16]], dropout_probs=[1.0], weight_penalties=[0.0, .001],
+                      batch_sizes=[50], num_steps=40, num_cross_folds=2, dropbox_path=str(tmp_path) + '/',
+                      data_loader=dl, check_test=True)
+        w.run()
+    res = w.val_results_df
+    assert len(res) == 2 and {'val_acc', 'val_auc', 'noisy_val_acc', 'clean_val_acc', 'val_acc_happiness'} <= set(res.columns)
+    assert ((res['val_acc'] >= 0) & (res['val_acc'] <= 1)).all()
+    assert w.model.engine.kernel_launches > 0
+
+    params = dict(w.list_of_param_settings[1])
+    dl.set_to_cross_validation_fold(1)
+    np.random.seed(3)
+    first = w.model
+    got = w.train_and_predict(params)
+    assert first.engine is None                      # closed when the next model was built
+    np.random.seed(3)
+    alone = NeuralNetwork(data_loader=dl, layer_sizes=params['architecture'], batch_size=params['batch_size'],
+                          learning_rate=params['learning_rate'], dropout_prob=params['dropout_prob'],
+                          weight_penalty=params['weight_penalty'], verbose=False, checkpoint_dir=None)
+    alone.train(num_steps=40, output_every_nth=5001)
+    assert np.array_equal(got, alone.predict(dl.val_X))
+    alone.close()

@@ -175,3 +175,56 @@ def test_svm_scoring_uses_one_embedding_pass(tmp_path):
     assert len(res) == 6 and all(r.shape == (1, 3) for r in res)
     for part in (cdl.val_X, cdl.noisy_val_X, cdl.clean_val_X):     # each SVM sees exactly its own rows' embeddings
         assert np.allclose(seen[len(part)], np.asarray(part)[:, :6] * 2.0)
+
+
+def test_nn_wrapper_grid_and_fold_protocol(tmp_path, monkeypatch):
+    """NNWrapper (comparison_algorithms/neural_net.py:407-631): 4 x 2 x 4 x 1 x 1 = 32 settings by default; one setting =
+    one fresh NeuralNetwork per fold (the previous engine closed first), trained num_steps, predicted on that fold's
+    validation rows (+ noisy / clean subsets), per-label columns in the result row; test_on_test scores TEST rows."""
+    from multimodalautoencoder_b200 import neural_net as nn
+    _, cdl = _fake_loaders()
+    w = nn.NNWrapper('synthetic.csv', dropbox_path=str(tmp_path) + '/', data_loader=cdl)
+    assert w.num_settings == 32
+    assert set(w.list_of_param_settings[0]) == {'architecture', 'dropout_prob', 'weight_penalty', 'learning_rate',
+                                                'batch_size'}
+    assert (w.classifier_name, w.optimize_for, w.min_or_max, w.check_test, w.check_noisy_data) == \
+        ('NN', 'val_acc', 'max', True, True)
+
+    log = []
+
+    class FakeNet:
+        def __init__(self, **kw):
+            self.kw, self.closed = kw, False
+            log.append(('new', kw['layer_sizes'], kw['batch_size'], len(kw['data_loader'].val_X)))
+
+        def train(self, num_steps, output_every_nth):
+            log.append(('train', num_steps, output_every_nth))
+
+        def predict(self, X):
+            log.append(('predict', len(X)))
+            return (np.asarray(X)[:, :cdl.num_labels] > 0.5).astype(np.float32)
+
+        def close(self):
+            self.closed = True
+            log.append(('close',))
+
+    monkeypatch.setattr(nn, 'NeuralNetwork', FakeNet)
+    w = nn.NNWrapper('synthetic.csv', layer_sizes=[[8, 4]], dropout_probs=[1.0], weight_penalties=[0.0, .01],
+                     num_steps=7, num_cross_folds=3, dropbox_path=str(tmp_path) + '/', data_loader=cdl)
+    assert w.num_settings == 2
+    row = w.get_cross_validation_results(dict(w.list_of_param_settings[0]))
+    assert [e[0] for e in log].count('new') == 3 and [e[0] for e in log].count('close') == 2
+    assert [e for e in log if e[0] == 'train'] == [('train', 7, 5001)] * 3
+    assert [e[0] for e in log].count('predict') == 9            # val + noisy + clean per fold
+    n = cdl.num_labels
+    want = {'val_acc', 'val_auc', 'val_f1', 'val_precision', 'val_recall', 'noisy_val_acc', 'noisy_val_auc',
+            'clean_val_acc', 'clean_val_auc'}
+    for label in nn.LABELS_TO_PREDICT[:n]:
+        want |= {p + label for p in ('val_acc_', 'val_auc_', 'noisy_val_acc_', 'noisy_val_auc_', 'clean_val_acc_',
+                                     'clean_val_auc_')}
+    assert want <= set(row) and 0.0 <= row['val_acc'] <= 1.0
+    del log[:]
+    preds = w.test_on_test(w.convert_param_dict_for_use({'architecture': '[8, 4]', 'batch_size': '100',
+                                                          'learning_rate': .001, 'dropout_prob': 1.0,
+                                                          'weight_penalty': 0.0}))
+    assert len(preds) == len(cdl.test_X) and log[1][1:3] == ([8, 4], 100)
