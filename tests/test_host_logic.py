@@ -228,3 +228,37 @@ def test_nn_wrapper_grid_and_fold_protocol(tmp_path, monkeypatch):
                                                           'learning_rate': .001, 'dropout_prob': 1.0,
                                                           'weight_penalty': 0.0}))
     assert len(preds) == len(cdl.test_X) and log[1][1:3] == ([8, 4], 100)
+
+
+def test_sweep_resumes_from_results_file(tmp_path, monkeypatch):
+    """cont=True (generic_wrapper.py:104-120 in the reference): settings already in the results CSV are skipped, the
+    new ones appended to the same file."""
+    from multimodalautoencoder_b200 import neural_net as nn
+    _, cdl = _fake_loaders()
+    trained = []
+
+    class FakeNet:
+        def __init__(self, **kw):
+            trained.append((tuple(kw['layer_sizes']), kw['weight_penalty']))
+
+        def train(self, num_steps, output_every_nth):
+            pass
+
+        def predict(self, X):
+            return (np.asarray(X)[:, :cdl.num_labels] > 0.5).astype(np.float32)
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(nn, 'NeuralNetwork', FakeNet)
+    kw = dict(layer_sizes=[[8, 4]], dropout_probs=[1.0], num_steps=1, num_cross_folds=2, check_test=False,
+              check_noisy_data=False, dropbox_path=str(tmp_path) + '/', data_loader=cdl)
+    w = nn.NNWrapper('synthetic.csv', weight_penalties=[0.0, .01], **kw)
+    w.run()
+    assert len(w.val_results_df) == 2 and len(trained) == 4
+    del trained[:]
+    w2 = nn.NNWrapper('synthetic.csv', weight_penalties=[0.0, .01, .001], cont=True, **kw)
+    assert w2.save_prefix == w.save_prefix and len(w2.val_results_df) == 2
+    w2.run()
+    assert len(w2.val_results_df) == 3
+    assert sorted(set(trained)) == [((8, 4), .001)]
