@@ -9,7 +9,8 @@ pandas >= 2 (the reference used DataFrame.from_csv / .as_matrix / .ix, all remov
 
 Differences, all opt-in or fixes:
   * DataLoader(df=...) accepts an in-memory DataFrame (synthetic data never touches the disk);
-  * persist_folds=False: the reference rewrote the input CSV after assigning folds (data_funcs.py:220-222);
+  * persist_folds=False opts out of the reference's rewrite of the input CSV after it assigns folds
+    (data_funcs.py:220-222; the default keeps it: a second loader of the same file must see the same folds);
   * per-row Python loops of the reference are vectorised where that cannot change results.
 """
 from __future__ import annotations
@@ -120,24 +121,48 @@ def remove_null_cols(df, features):
     return df, features
 
 
+def _gap_blocks(columns):
+    """The column blocks the reference's row loop walks (:733-766), which depend on the column layout only:
+    (first position, end position, feature columns counted) per run of equal feature prefixes.  Kept as the reference
+    computes them: the first block starts at POSITION 2 whatever precedes it (the loop assumes two leading bookkeeping
+    columns), a block's fill range is positional and so takes in any non-feature column that sits inside it, and the
+    LAST block is never closed -- its rows are never filled."""
+    skip = ('user_id', 'timestamp', 'logistics', 'label', 'dataset', 'Label')
+    columns = list(columns)
+    current, start, members, blocks = get_feat_prefix(columns[2], subdivide_phys=True), 2, [], []
+    for pos, feat in enumerate(columns):
+        if any(tok in feat for tok in skip):
+            continue
+        prefix = get_feat_prefix(feat, subdivide_phys=True)
+        if prefix != current:
+            if not members:
+                raise ZeroDivisionError("float division by zero")     # the reference divides by the (empty) block's size
+            blocks.append((start, pos, members))
+            start, members = pos, []
+        members.append(feat)
+        current = prefix
+    return blocks
+
+
 def fill_gaps_in_modalities(df, fill_value, suppress_output=False, verbose=False):
-    """Rows missing > 80 % of one modality get that whole modality set to fill_value (:712-769)."""
+    """Rows missing > 80 % of one modality get that modality's column range set to fill_value (:712-769) -- the
+    reference's per-row, per-column Python loop as one vectorised pass per block, with its block rules (_gap_blocks)."""
     df = df.copy()
-    feats = get_wanted_feats_from_df(df)
-    groups = {}
-    for f in feats:
-        groups.setdefault(get_feat_prefix(f, subdivide_phys=True), []).append(f)
     filled = 0
-    for prefix, cols in groups.items():
-        frac = df[cols].isnull().mean(axis=1)
-        rows = frac > 0.8
+    for start, end, members in _gap_blocks(df.columns.values):
+        rows = (df[members].isnull().sum(axis=1) / float(len(members)) > 0.8).to_numpy()
         if rows.any():
-            df.loc[rows, cols] = fill_value
+            for pos in range(start, end):
+                col = df.columns[pos]
+                if not pd.api.types.is_float_dtype(df[col].dtype):
+                    df[col] = df[col].astype(object)
+                df.iloc[np.nonzero(rows)[0], pos] = fill_value
             filled += int(rows.sum())
             if verbose:
-                print("Filled modality %s in %d rows" % (prefix, int(rows.sum())))
+                print("Filled", get_feat_prefix(members[0], subdivide_phys=True), "(index", start, "to", end, ") in",
+                      int(rows.sum()), "rows")
     if not suppress_output:
-        print("Filled gaps in %d (row, modality) pairs with %s" % (filled, fill_value))
+        print("Filled gaps in", filled, "rows with", fill_value)
     return df
 
 
@@ -164,7 +189,7 @@ class DataLoader:
     def __init__(self, filename=None, supervised=True, suppress_output=False, cross_validation=False,
                  normalize_and_fill=True, normalization='between_0_and_1', fill_missing_with=0,
                  fill_gaps_with=None, extract_modalities=True, subdivide_physiology_features=False,
-                 wanted_label=None, labels_to_sign=False, separate_noisy_data=True, df=None, persist_folds=False):
+                 wanted_label=None, labels_to_sign=False, separate_noisy_data=True, df=None, persist_folds=True):
         self.filename = filename
         self.supervised = supervised
         self.normalize_and_fill = normalize_and_fill

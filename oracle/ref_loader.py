@@ -8,7 +8,8 @@ TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  Only tests/, smoke() and bench.py's re
     m.session.run([m.opt_step], feed)          # the reference's own graph, differentiated by torch.autograd
 
 `make_loader` builds the reference's own DataLoader object without running its CSV/pandas constructor
-(`DataLoader.__init__` needs APIs removed from pandas long ago): the instance is allocated with
+(`DataLoader.__init__` needs APIs removed from pandas long ago; tests/test_loader_vs_ref.py runs it under
+`pandas_compat.legacy_pandas()`): the instance is allocated with
 `object.__new__` and given exactly the attributes the model reads, so the batch
 sampling (`data_funcs.py:161-195`) and the missing-block rule (`:366-381`) that run are the reference's.
 """
