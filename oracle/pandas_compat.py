@@ -7,6 +7,7 @@ Semantics follow the pandas 0.2x documentation of the removed calls:
   * df.as_matrix()            == df.values
   * df.ix[row, col]           -- label based, with positional fallback for an integer key on a non-integer axis
                                   (the reference writes `df.ix[row_label, column_position] = v`, data_funcs.py:754)
+  * df.append(row, ignore_index=True) == concat([df, DataFrame([row])], ignore_index=True)   (generic_wrapper.py:276)
   * series[[i, j, ...]] = v   -- integer keys on a non-integer index are positions
                                   (the reference writes `xfill[missing_idxs] = Xbar[i, missing_idxs]`, data_funcs.py:338)
 """
@@ -72,6 +73,11 @@ def legacy_pandas():
         if not hasattr(pd.DataFrame, 'as_matrix'):
             pd.DataFrame.as_matrix = lambda self, columns=None: (self if columns is None else self[columns]).values
             added.append('as_matrix')
+        if not hasattr(pd.DataFrame, 'append'):
+            def _append(self, other, ignore_index=False):
+                other = pd.DataFrame([other]) if isinstance(other, (dict, pd.Series)) else other
+                return pd.concat([self, other], ignore_index=ignore_index)
+            pd.DataFrame.append = _append; added.append('append')
         if not hasattr(pd.DataFrame, 'ix'):
             pd.DataFrame.ix = property(_Ix); added.append('ix')
         yield

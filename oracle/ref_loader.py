@@ -50,8 +50,9 @@ def _stub_matplotlib():
 
 
 class Reference:
-    def __init__(self, tf, mmae, data_funcs, neural_net=None):
+    def __init__(self, tf, mmae, data_funcs, neural_net=None, generic_wrapper=None, helper_funcs=None):
         self.tf, self.mmae, self.data_funcs, self.neural_net = tf, mmae, data_funcs, neural_net
+        self.generic_wrapper, self.helper_funcs = generic_wrapper, helper_funcs
 
     def make_loader(self, train_X, val_X, modality_starts, modality_names, train_Y=None, val_Y=None, num_labels=None,
                     test_X=None, test_Y=None):
@@ -112,10 +113,10 @@ def load_reference(dtype=None):
             df = _load_module('mmae_ref_data_funcs', os.path.join(REF_DIR, 'data_funcs.py'))
             sys.modules['data_funcs'] = df
             mm = _load_module('mmae_ref_multimodal_autoencoder', os.path.join(REF_DIR, 'multimodal_autoencoder.py'))
-            nn = None
+            nn = gw = hf = None
             try:       # the plain MLP classifier (comparison_algorithms/neural_net.py) and what it imports
-                sys.modules['helper_funcs'] = _load_module('mmae_ref_helper_funcs', os.path.join(REF_DIR, 'helper_funcs.py'))
-                sys.modules['generic_wrapper'] = _load_module('mmae_ref_generic_wrapper', os.path.join(REF_DIR, 'generic_wrapper.py'))
+                sys.modules['helper_funcs'] = hf = _load_module('mmae_ref_helper_funcs', os.path.join(REF_DIR, 'helper_funcs.py'))
+                sys.modules['generic_wrapper'] = gw = _load_module('mmae_ref_generic_wrapper', os.path.join(REF_DIR, 'generic_wrapper.py'))
                 nn = _load_module('mmae_ref_neural_net', os.path.join(REF_DIR, 'neural_net.py'))
             except Exception as e:       # noqa: BLE001 -- the MMAE pinning does not depend on it
                 print('oracle/_ref: neural_net.py not loadable:', repr(e)[:200])
@@ -125,7 +126,7 @@ def load_reference(dtype=None):
                     sys.modules.pop(k, None)
                 else:
                     sys.modules[k] = v
-        _cached = Reference(tf, mm, df, nn)
+        _cached = Reference(tf, mm, df, nn, gw, hf)
     if dtype is not None:
         _cached.tf.set_default_dtype(dtype)
     return _cached
