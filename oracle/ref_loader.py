@@ -50,9 +50,12 @@ def _stub_matplotlib():
 
 
 class Reference:
-    def __init__(self, tf, mmae, data_funcs, neural_net=None, generic_wrapper=None, helper_funcs=None):
+    def __init__(self, tf, mmae, data_funcs, neural_net=None, generic_wrapper=None, helper_funcs=None,
+                 autoencoder_wrapper=None, autoencoder_classification_wrapper=None):
         self.tf, self.mmae, self.data_funcs, self.neural_net = tf, mmae, data_funcs, neural_net
         self.generic_wrapper, self.helper_funcs = generic_wrapper, helper_funcs
+        self.autoencoder_wrapper = autoencoder_wrapper
+        self.autoencoder_classification_wrapper = autoencoder_classification_wrapper
 
     def make_loader(self, train_X, val_X, modality_starts, modality_names, train_Y=None, val_Y=None, num_labels=None,
                     test_X=None, test_Y=None):
@@ -100,7 +103,8 @@ def load_reference(dtype=None):
             sys.path.pop(0)
         if not build_ref.build():
             return None
-        saved = {k: sys.modules.get(k) for k in ('tensorflow', 'matplotlib', 'matplotlib.pyplot', 'data_funcs', 'helper_funcs', 'generic_wrapper')}
+        saved = {k: sys.modules.get(k) for k in ('tensorflow', 'matplotlib', 'matplotlib.pyplot', 'data_funcs', 'helper_funcs',
+                                                  'generic_wrapper', 'multimodal_autoencoder')}
         tf = _load_module('mmae_tf1_shim', os.path.join(SHIM_DIR, 'tensorflow', '__init__.py'))
         try:
             sys.modules['tensorflow'] = tf
@@ -120,13 +124,21 @@ def load_reference(dtype=None):
                 nn = _load_module('mmae_ref_neural_net', os.path.join(REF_DIR, 'neural_net.py'))
             except Exception as e:       # noqa: BLE001 -- the MMAE pinning does not depend on it
                 print('oracle/_ref: neural_net.py not loadable:', repr(e)[:200])
+            aw = acw = None
+            try:       # the two grid-search drivers of the MMAE
+                sys.modules['multimodal_autoencoder'] = mm
+                aw = _load_module('mmae_ref_autoencoder_wrapper', os.path.join(REF_DIR, 'autoencoder_wrapper.py'))
+                acw = _load_module('mmae_ref_autoencoder_classification_wrapper',
+                                   os.path.join(REF_DIR, 'autoencoder_classification_wrapper.py'))
+            except Exception as e:       # noqa: BLE001
+                print('oracle/_ref: wrapper modules not loadable:', repr(e)[:200])
         finally:
             for k, v in saved.items():          # leave no fake `tensorflow` / `matplotlib` behind for other importers
                 if v is None:
                     sys.modules.pop(k, None)
                 else:
                     sys.modules[k] = v
-        _cached = Reference(tf, mm, df, nn, gw, hf)
+        _cached = Reference(tf, mm, df, nn, gw, hf, aw, acw)
     if dtype is not None:
         _cached.tf.set_default_dtype(dtype)
     return _cached
